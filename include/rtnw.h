@@ -1,0 +1,253 @@
+/*
+ * rtnw.h — C-ABI of the B200-native replacement for the per-pixel path-tracing sample loop of
+ * EStormLynn/Peter-Shirley-Ray-Tracing-the-next-week.
+ *
+ * The reference has no FFI: its seam is the C++ object API (`hitable`, `material`, `texture`, `camera`)
+ * plus the sample loop in `Peter-Shirley-Project Code/main.cpp:299-332` (PSC/ below).  This header is the
+ * boundary a maintainer binds instead of that loop:
+ *
+ *   host C++ scene graph (same class names/ctors as the PSC headers)  --flatten-->  rtnw_scene_desc (SoA tables)
+ *   rtnw_scene_upload()  -> tables resident in HBM
+ *   rtnw_render()        -> replaces PSC/main.cpp:304-313 for every (i,j,s); returns float RGB sums
+ *   rtnw_trace()         -> replaces one `world->hit(r,tmin,tmax,rec)` (PSC/main.cpp:27) per ray, for parity
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Every call returns RTNW_OK (0) or a negative status and
+ * never throws across the boundary; rtnw_last_error() gives a thread-local message.
+ * There is no CPU fallback: every compute entry point fails with RTNW_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RTNW_H_
+#define RTNW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTNW_ABI_VERSION 3
+
+enum rtnw_status {
+    RTNW_OK = 0,
+    RTNW_ERR_INVALID = -1,     /* bad argument / malformed tables            */
+    RTNW_ERR_CUDA = -2,        /* CUDA runtime error or no usable device     */
+    RTNW_ERR_UNSUPPORTED = -3, /* scene nesting the flattened form cannot express */
+    RTNW_ERR_NOMEM = -4
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * Flattened scene tables.  All records are 16-byte multiples so the device reads them with 128-bit loads.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Primitive kinds (one 32-byte slot each; a moving sphere takes two consecutive slots). */
+enum rtnw_prim_kind {
+    RTNW_PRIM_SPHERE = 0,        /* PSC/sphere.h:10-58     f = {cx,cy,cz,r}                                */
+    RTNW_PRIM_MOVING_SPHERE = 1, /* PSC/sphere.h:61-118    f = {c0x,c0y,c0z,r,t0,t1}; next slot f={c1x,c1y,c1z} */
+    RTNW_PRIM_RECT_XY = 2,       /* PSC/aarect.h:11-22     f = {x0,x1,y0,y1,k}                             */
+    RTNW_PRIM_RECT_XZ = 3,       /* PSC/aarect.h:24-34     f = {x0,x1,z0,z1,k}                             */
+    RTNW_PRIM_RECT_YZ = 4,       /* PSC/aarect.h:36-46     f = {y0,y1,z0,z1,k}                             */
+    RTNW_PRIM_BOX = 5,           /* PSC/box.h:11-38        f = {p0x,p0y,p0z,p1x,p1y,p1z}; six faces in the reference's order */
+    RTNW_PRIM_MEDIUM = 6,        /* PSC/constant_medium.h  f[0]=density, f[1],f[2] = int32 bit patterns: first boundary slot, slot count */
+    RTNW_PRIM_EXT = 7            /* continuation slot of the previous primitive                              */
+};
+
+/* kx word: bits 0-2 kind, bit 3 flip_normals parity (PSC/hitable.h:39-54), bits 4-31 xform chain (index of its
+ * first op in the xform table; 0 = identity). */
+#define RTNW_KX(kind, flip, xform) ((uint32_t)(kind) | ((uint32_t)((flip) & 1) << 3) | ((uint32_t)(xform) << 4))
+#define RTNW_KX_KIND(kx) ((kx) & 7u)
+#define RTNW_KX_FLIP(kx) (((kx) >> 3) & 1u)
+#define RTNW_KX_XFORM(kx) ((kx) >> 4)
+
+typedef struct rtnw_prim {
+    float f[6];
+    uint32_t kx;  /* RTNW_KX(kind, flip, xform) */
+    int32_t mat;  /* material index (phase function for a medium); -1 for boundary-only / EXT slots */
+} rtnw_prim; /* 32 B */
+
+/* Transform chain ops, applied to the ray first-to-last and to the hit last-to-first
+ * (PSC/hitable.h:57-83 translate, :85-150 rotate_y).  Op 0 of the table is a reserved identity. */
+enum rtnw_xform_kind { RTNW_XF_END = 0, RTNW_XF_TRANSLATE = 1, RTNW_XF_ROTATE_Y = 2 };
+typedef struct rtnw_xform_op {
+    float a, b, c;   /* TRANSLATE: offset xyz; ROTATE_Y: a = sin_theta, b = cos_theta */
+    uint32_t kind;   /* bits 0-7 rtnw_xform_kind; bits 8-31 (first op of a chain only) number of ops in the chain */
+} rtnw_xform_op; /* 16 B */
+
+/* BVH node = one reference bvh_node (PSC/bvh.h:11-54) holding BOTH children's boxes, so that entering a child
+ * is decided by that child's own aabb::hit exactly as in the reference (leaves are never box-tested there).
+ * Child ref >= 0: index of an internal node. ref < 0 and != RTNW_REF_NONE: leaf, first prim slot = ~ref,
+ * slot count in lcount/rcount (list semantics inside the range).  RTNW_REF_NONE: absent (n==1 nodes, where the
+ * reference sets left == right, PSC/bvh.h:106-108). */
+#define RTNW_REF_NONE INT32_MIN
+typedef struct rtnw_bvh_node {
+    float lmin[3]; int32_t left;
+    float lmax[3]; int32_t right;
+    float rmin[3]; int32_t lcount;
+    float rmax[3]; int32_t rcount;
+} rtnw_bvh_node; /* 64 B */
+
+/* World sequence: the top-level hitable_list (PSC/hitable_list.h:20-32) after inlining nested lists.
+ * Items are evaluated in order with the narrowing closest_so_far of the reference's list. */
+enum rtnw_item_kind { RTNW_ITEM_PRIMS = 0, RTNW_ITEM_BVH = 1 };
+typedef struct rtnw_item {
+    uint32_t kind;    /* rtnw_item_kind */
+    uint32_t xform;   /* chain applied before entering the item (e.g. translate(rotate_y(bvh_node))) */
+    int32_t first;    /* PRIMS: first prim slot; BVH: root node index */
+    int32_t count;    /* PRIMS: slot count; BVH: number of nodes in this tree */
+    float bmin[3]; uint32_t flip; /* BVH: root box (the root bvh_node's own box); flip parity pushed to prims already (informational) */
+    float bmax[3]; uint32_t pad;
+} rtnw_item; /* 48 B */
+
+enum rtnw_material_kind {
+    RTNW_MAT_LAMBERTIAN = 0,   /* PSC/material.h:61-72   tex = albedo texture */
+    RTNW_MAT_METAL = 1,        /* PSC/material.h:74-85   albedo rgb, f = fuzz (already clamped to <= 1) */
+    RTNW_MAT_DIELECTRIC = 2,   /* PSC/material.h:87-123  f = ref_idx */
+    RTNW_MAT_DIFFUSE_LIGHT = 3,/* PSC/material.h:126-139 tex = emit texture */
+    RTNW_MAT_ISOTROPIC = 4     /* PSC/material.h:142-151 tex = albedo texture */
+};
+typedef struct rtnw_material {
+    uint32_t kind; int32_t tex; float f; uint32_t pad0;
+    float albedo[3]; uint32_t pad1;
+} rtnw_material; /* 32 B */
+
+enum rtnw_texture_kind {
+    RTNW_TEX_CONSTANT = 0, /* PSC/texture.h:16-28   c = color */
+    RTNW_TEX_CHECKER = 1,  /* PSC/texture.h:30-45   i0 = even texture, i1 = odd texture */
+    RTNW_TEX_NOISE = 2,    /* PSC/texture.h:47-59   c[0] = scale */
+    RTNW_TEX_IMAGE = 3     /* PSC/surface_texture.h i0 = byte offset into the image pool, i1 = nx, i2 = ny (RGB8) */
+};
+typedef struct rtnw_texture {
+    uint32_t kind; int32_t i0, i1, i2;
+    float c[3]; uint32_t pad;
+} rtnw_texture; /* 32 B */
+
+/* Borrowed host pointers; rtnw_scene_upload copies everything, the caller may free afterwards. */
+typedef struct rtnw_scene_desc {
+    uint32_t abi_version;          /* RTNW_ABI_VERSION */
+    int32_t n_items;      const rtnw_item* items;
+    int32_t n_nodes;      const rtnw_bvh_node* nodes;
+    int32_t n_prim_slots; const rtnw_prim* prims;
+    const int32_t* prim_ids;       /* per slot: leaf id (creation-order index of the leaf handed to the list/BVH); parity only */
+    int32_t n_xform_ops;  const rtnw_xform_op* xforms;
+    int32_t n_materials;  const rtnw_material* materials;
+    int32_t n_textures;   const rtnw_texture* textures;
+    uint64_t image_bytes; const uint8_t* images;
+    const float* perlin_ranvec;    /* 256 x 3 floats, PSC/perlin.h:82-87 */
+    const int32_t* perlin_perm_x;  /* 256 each, PSC/perlin.h:99-106 */
+    const int32_t* perlin_perm_y;
+    const int32_t* perlin_perm_z;
+} rtnw_scene_desc;
+
+/* camera — the fields PSC/camera.h:21-39 computes, passed through verbatim. */
+typedef struct rtnw_camera {
+    float origin[3];
+    float lower_left_corner[3];
+    float horizontal[3];
+    float vertical[3];
+    float u[3], v[3], w[3];
+    float lens_radius;
+    float time0, time1;
+} rtnw_camera;
+
+enum rtnw_background { RTNW_BG_BLACK = 0 /* PSC/main.cpp:44 */, RTNW_BG_SKY = 1 /* TNW/Chapter01_Motion Blur.cpp:29-31 */ };
+
+/* render flags */
+#define RTNW_F_DE_NAN        1u  /* per-sample NaN->0, PSC/main.cpp:232-242,311 */
+#define RTNW_F_EMIT          2u  /* add material emitted(), PSC/main.cpp:33 (off only for the Ch01/Ch03 snapshots) */
+#define RTNW_F_CULL_NARROW   4u  /* BVH: cull subtrees against best_t*(1+margin) instead of the reference's un-narrowed range.
+                                    Same closest hit unless float rounding exceeds the margin; off = reference-exact traversal. */
+#define RTNW_F_COUNTERS      8u  /* fill the optional work counters in rtnw_stats */
+
+typedef struct rtnw_render_params {
+    int32_t nx, ny;
+    int32_t sample_begin;   /* this call renders samples s = sample_begin + k*sample_stride, k in [0, sample_count) */
+    int32_t sample_count;
+    int32_t sample_stride;  /* multi-GPU spp split: rank g of G uses begin=g, stride=G */
+    int32_t max_depth;      /* 50, PSC/main.cpp:34 */
+    float t_min;            /* 0.001, PSC/main.cpp:27 (0.0 / 0.01 in the chapter snapshots) */
+    float t_max;            /* MAXFLOAT */
+    uint32_t background;    /* rtnw_background */
+    uint32_t flags;         /* RTNW_F_* */
+    uint64_t seed;          /* Philox key; the sample stream is a function of (seed, pixel, sample) only */
+} rtnw_render_params;
+
+typedef struct rtnw_stats {
+    uint64_t paths;        /* (i,j,s) samples, PSC/main.cpp:304 */
+    uint64_t rays;         /* top-level closest-hit queries, PSC/main.cpp:27 */
+    uint64_t box_tests;    /* RTNW_F_COUNTERS only */
+    uint64_t prim_tests;   /* RTNW_F_COUNTERS only */
+    float kernel_ms;       /* device time of the render kernel(s), CUDA events */
+    float total_ms;        /* including copies done inside the call */
+    int32_t kernel_launches;
+    int32_t pad;
+} rtnw_stats;
+
+typedef struct rtnw_ray {
+    float origin[3];
+    float direction[3];
+    float time;
+    uint32_t key;          /* stream id for media free-flight draws in rtnw_trace (Philox pixel slot) */
+} rtnw_ray; /* 32 B */
+
+typedef struct rtnw_hit {
+    int32_t prim_id;       /* leaf id, -1 = miss */
+    int32_t sub_id;        /* box face 0..5 (reference order, PSC/box.h:28-33), else 0 */
+    float t;
+    float p[3];
+    float normal[3];
+    float u, v;
+    int32_t mat_id;
+} rtnw_hit; /* 48 B */
+
+typedef struct rtnw_ctx rtnw_ctx;       /* one GPU + its stream */
+typedef struct rtnw_scene rtnw_scene;   /* device-resident copy of a scene_desc */
+
+const char* rtnw_last_error(void);
+int rtnw_abi_version(void);
+/* number of CUDA devices with compute capability 10.x; 0 if none (never an error) */
+int rtnw_device_count(void);
+
+int rtnw_ctx_create(int device, rtnw_ctx** out);
+int rtnw_ctx_destroy(rtnw_ctx* ctx);
+/* copy the device properties the roofline needs: sm_count, clock kHz, smem per block optin, l2 bytes */
+int rtnw_ctx_info(rtnw_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t* smem_optin, int32_t* l2_bytes);
+
+int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out);
+int rtnw_scene_free(rtnw_ctx* ctx, rtnw_scene* scene);
+
+/* Replaces PSC/main.cpp:304-313 over all pixels.  accum_rgb (host, nx*ny*3 floats, index (j*nx+i)*3+c with the
+ * reference's j, i.e. j=0 is the bottom row) receives per-pixel SUMS over this call's samples; the host epilogue
+ * (PSC/main.cpp:315-330) divides by ns, applies sqrt gamma and quantises.  Device->host copy is inside the call. */
+int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, const rtnw_render_params* params,
+                float* accum_rgb, rtnw_stats* stats);
+
+/* Same, but accum_rgb_dev is DEVICE memory owned by the caller (e.g. a torch tensor that is then reduced with
+ * NCCL); the buffer is overwritten.  cuda_stream may be NULL (ctx stream).  Synchronous on return. */
+int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam,
+                       const rtnw_render_params* params, float* accum_rgb_dev, void* cuda_stream, rtnw_stats* stats);
+
+/* Deterministic closest-hit query: one `world->hit(r, t_min, t_max, rec)` per ray (PSC/main.cpp:27).  Host buffers.
+ * flags: RTNW_F_CULL_NARROW selects the narrowed traversal; media draw their free-flight number from
+ * Philox(seed, ray.key, medium leaf id), so results do not depend on traversal order. */
+int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, size_t n, float t_min, float t_max,
+               uint32_t flags, uint64_t seed, rtnw_hit* out);
+
+/* texture::value(u,v,p) for n points; uvp = n x 5 floats {u,v,px,py,pz}; rgb_out = n x 3 (PSC/texture.h, surface_texture.h) */
+int rtnw_eval_texture(rtnw_ctx* ctx, const rtnw_scene* scene, int32_t tex_id, const float* uvp, size_t n, float* rgb_out);
+/* perlin::noise (which=0) / perlin::turb depth 7 (which=1) at n points xyz (PSC/perlin.h:43-74) */
+int rtnw_eval_perlin(rtnw_ctx* ctx, const rtnw_scene* scene, int32_t which, const float* xyz, size_t n, float* out);
+
+/* material::emitted + material::scatter for n (ray, hit) pairs; hit[i].mat_id selects the material.
+ * Random draws come from the sequential Philox stream (seed, pixel=i, sample=0) starting at draw 0.
+ * out_scattered[i] = scattered ray; out_atten = n x 3; out_emitted = n x 3; out_flag[i] = scatter's return value. */
+int rtnw_scatter(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays_in, const rtnw_hit* hits, size_t n,
+                 uint64_t seed, rtnw_ray* out_scattered, float* out_atten, float* out_emitted, int32_t* out_flag);
+
+/* camera::get_ray for n samples (PSC/camera.h:41-56 + the jitter of PSC/main.cpp:305-306):
+ * ij = n x 2 int32 {i, j}; sample s = sample index; rays_out[n]. Draw order as in rtnw_render. */
+int rtnw_camera_rays(rtnw_ctx* ctx, const rtnw_camera* cam, int32_t nx, int32_t ny, const int32_t* ij,
+                     const int32_t* sample, size_t n, uint64_t seed, rtnw_ray* rays_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTNW_H_ */

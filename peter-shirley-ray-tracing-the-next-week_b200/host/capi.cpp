@@ -1,0 +1,144 @@
+// extern "C" surface of librtnw_host.so (include/rtnw_host.h).
+#include "rtnw_host.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "rtnw/flatten.hpp"
+#include "scenes/chapter_scenes.hpp"
+
+struct rtnw_host_scene {
+    rtnw::flat_scene flat;
+    rtnw_scene_desc desc;
+    rtnw_scenes::view view;
+};
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+}  // namespace
+
+extern "C" {
+
+const char* rtnw_host_last_error(void) { return g_err.c_str(); }
+
+int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
+    if (!name_c || !out) return fail(RTNW_ERR_INVALID, "null argument");
+    std::string name(name_c);
+    bool wrap = false;
+    const size_t plus = name.find("+bvh");
+    if (plus != std::string::npos) {
+        wrap = true;
+        name.erase(plus);
+    }
+    // never-seeded drand48 state (glibc: X0 = 0x1234ABCD330E), then the tables the reference draws before main()
+    srand48(0x1234ABCD);
+    perlin::regenerate();
+
+    using namespace rtnw_scenes;
+    hitable* world = nullptr;
+    view v;
+    if (name == "ch01_random") { world = random_scene_ch01(); v = view_ch01(); }
+    else if (name == "two_perlin") { world = two_perlin_spheres(); v = view_two_perlin(); }
+    else if (name == "cornell_box") { world = cornell_box(); v = view_cornell(); }
+    else if (name == "cornell_smoke") { world = cornell_smoke(); v = view_cornell(); }
+    else if (name == "final") { world = final_scene(); v = view_final(); }
+    else if (name == "final_northstar") { world = final_northstar(); v = view_final(); }
+    else if (name == "simple_light") { world = simple_light(); v = view_two_perlin(); v.sky = false; v.emit = true; }
+    else if (name == "two_spheres") { world = two_spheres(); v = view_cornell(); v.sky = true; }
+    else if (name == "earth") { world = earth(); v = view_cornell(); }
+    else return fail(RTNW_ERR_INVALID, "unknown scene name: " + name);
+    if (wrap) world = wrap_in_bvh(world, 0, 1);
+
+    rtnw_host_scene* s = new rtnw_host_scene();
+    const int rc = rtnw::flatten(world, s->flat);
+    if (rc != RTNW_OK) {
+        const std::string msg = s->flat.error;
+        delete s;
+        return fail(rc, msg);
+    }
+    s->desc = s->flat.desc();
+    s->view = v;
+    *out = s;
+    return RTNW_OK;
+}
+
+void rtnw_host_scene_free(rtnw_host_scene* s) { delete s; }
+
+const rtnw_scene_desc* rtnw_host_scene_desc(const rtnw_host_scene* s) { return s ? &s->desc : nullptr; }
+
+int32_t rtnw_host_scene_leaf_count(const rtnw_host_scene* s) { return s ? s->flat.n_leaves : 0; }
+
+int rtnw_host_scene_camera(const rtnw_host_scene* s, int32_t nx, int32_t ny, rtnw_camera* cam) {
+    if (!s || !cam || nx <= 0 || ny <= 0) return fail(RTNW_ERR_INVALID, "bad camera arguments");
+    rtnw::to_c_camera(rtnw_scenes::make_camera(s->view, nx, ny), *cam);
+    return RTNW_OK;
+}
+
+int rtnw_host_scene_view(const rtnw_host_scene* s, rtnw_host_view* out) {
+    if (!s || !out) return fail(RTNW_ERR_INVALID, "null argument");
+    out->nx = s->view.nx;
+    out->ny = s->view.ny;
+    out->ns = s->view.ns;
+    out->t_min = s->view.t_min;
+    out->background = s->view.sky ? RTNW_BG_SKY : RTNW_BG_BLACK;
+    out->flags = (s->view.emit ? RTNW_F_EMIT : 0u) | (s->view.de_nan ? RTNW_F_DE_NAN : 0u);
+    return RTNW_OK;
+}
+
+int rtnw_host_make_camera(const float lookfrom[3], const float lookat[3], const float vup[3], float vfov, float aspect,
+                          float aperture, float focus_dist, float t0, float t1, rtnw_camera* cam) {
+    if (!lookfrom || !lookat || !vup || !cam) return fail(RTNW_ERR_INVALID, "null argument");
+    camera c(vec3(lookfrom[0], lookfrom[1], lookfrom[2]), vec3(lookat[0], lookat[1], lookat[2]), vec3(vup[0], vup[1], vup[2]),
+             vfov, aspect, aperture, focus_dist, t0, t1);
+    rtnw::to_c_camera(c, *cam);
+    return RTNW_OK;
+}
+
+// PSC/main.cpp:315-325
+static inline void quantize_pixel(const float* sum, int32_t ns, int clamp255, int32_t out[3]) {
+    vec3 col(sum[0], sum[1], sum[2]);
+    col /= float(ns);
+    col = vec3(std::sqrt(col[0]), std::sqrt(col[1]), std::sqrt(col[2]));
+    for (int c = 0; c < 3; ++c) {
+        int v = int(255.99 * col[c]);
+        if (clamp255 && v > 255) v = 255;
+        out[c] = v;
+    }
+}
+
+int rtnw_host_quantize(const float* sums, int32_t nx, int32_t ny, int32_t ns, int32_t clamp255, int32_t* rgb_out) {
+    if (!sums || !rgb_out || nx <= 0 || ny <= 0 || ns <= 0) return fail(RTNW_ERR_INVALID, "bad quantize arguments");
+    size_t o = 0;
+    for (int j = ny - 1; j >= 0; --j)
+        for (int i = 0; i < nx; ++i, o += 3) quantize_pixel(sums + 3 * ((size_t)j * nx + i), ns, clamp255, rgb_out + o);
+    return RTNW_OK;
+}
+
+int rtnw_host_write_ppm(const char* path, const float* sums, int32_t nx, int32_t ny, int32_t ns, int32_t clamp255, int32_t binary) {
+    if (!path || !sums || nx <= 0 || ny <= 0 || ns <= 0) return fail(RTNW_ERR_INVALID, "bad ppm arguments");
+    FILE* f = std::fopen(path, binary ? "wb" : "w");
+    if (!f) return fail(RTNW_ERR_INVALID, std::string("cannot open ") + path);
+    std::fprintf(f, "%s\n%d %d\n255\n", binary ? "P6" : "P3", nx, ny);
+    for (int j = ny - 1; j >= 0; --j) {
+        for (int i = 0; i < nx; ++i) {
+            int32_t q[3];
+            quantize_pixel(sums + 3 * ((size_t)j * nx + i), ns, binary ? 1 : clamp255, q);
+            if (binary) {
+                const unsigned char b[3] = {(unsigned char)q[0], (unsigned char)q[1], (unsigned char)q[2]};
+                std::fwrite(b, 1, 3, f);
+            } else {
+                std::fprintf(f, "%d %d %d\n", q[0], q[1], q[2]);
+            }
+        }
+    }
+    std::fclose(f);
+    return RTNW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+// The reference API has four virtuals that do arithmetic on the hot path (hitable::hit, material::scatter,
+// material::emitted, texture::value; PSC/hitable.h:34, PSC/material.h:54-57, PSC/texture.h:13).  In this
+// framework they have no CPU implementation: a bridge forwards single calls to the GPU library
+// (rtnw_trace / rtnw_scatter / rtnw_eval_texture).  Without an installed bridge the calls abort loudly.
+#ifndef RTNW_DEVICE_BRIDGE_HPP_
+#define RTNW_DEVICE_BRIDGE_HPP_
+
+#include "rtnw/scene.hpp"
+
+namespace rtnw {
+struct device_bridge {
+    bool (*hit)(const hitable*, const ray&, float, float, hit_record&) = nullptr;
+    bool (*scatter)(const material*, const ray&, const hit_record&, vec3&, ray&) = nullptr;
+    vec3 (*emitted)(const material*, float, float, const vec3&) = nullptr;
+    vec3 (*value)(const texture*, float, float, const vec3&) = nullptr;
+};
+void set_device_bridge(const device_bridge& b);
+const device_bridge& get_device_bridge();
+}  // namespace rtnw
+
+#endif
