@@ -1,0 +1,794 @@
+// rtnw_cuda.cu — librtnw.so: sm_100a kernels + the C-ABI of include/rtnw.h.
+//
+// Replaces the sample loop of the reference (PSC/main.cpp:299-313) and everything it calls.  There is no CPU
+// implementation in this library: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rtnw.h"
+#include "rtnw_device.cuh"
+
+using namespace rtnw_dev;
+
+#ifndef RTNW_BLOCK
+#define RTNW_BLOCK 128
+#endif
+
+// ================================================================================================ kernels
+struct render_args {
+    scene_view S;
+    rtnw_camera cam;
+    rtnw_render_params p;
+    float* accum;                 // nx*ny*3 sums, index (j*nx+i)*3+c
+    unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests
+};
+
+// One thread = one pixel at a time: its samples are traced back to back and summed in sample order, exactly like
+// `col += temp` in PSC/main.cpp:304-313, so a pixel's sum does not depend on scheduling.  Threads are persistent:
+// a lane that finishes its pixel pulls the next one from a global counter (warp-aggregated), so a warp stays full
+// until the image is exhausted; a lane whose path ends starts the next sample of its pixel in the same iteration
+// of the warp loop (path regeneration), which absorbs the 51-bounce tail.
+template <bool COUNT>
+__global__ void __launch_bounds__(RTNW_BLOCK) k_render(const render_args P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int nx = P.p.nx, ny = P.p.ny;
+    const unsigned long long npix = (unsigned long long)nx * (unsigned long long)ny;
+    const uint32_t k0 = (uint32_t)P.p.seed, k1 = (uint32_t)(P.p.seed >> 32);
+    const bool narrow = (P.p.flags & RTNW_F_CULL_NARROW) != 0;
+    const bool emit = (P.p.flags & RTNW_F_EMIT) != 0;
+    const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
+    const bool sky = P.p.background == RTNW_BG_SKY;
+
+    bool alive = true, need = true;
+    int pix = -1, k = 0, depth = 0;
+    f3 col = mk3(0.f, 0.f, 0.f), L = col, T = col;
+    ray_t r;
+    r.o = col; r.d = col; r.time = 0.f;
+    rng_t g;
+    g.begin(k0, k1, 0, 0);
+    unsigned long long n_rays = 0;
+    trav_counters cnt;
+    cnt.box_tests = 0; cnt.prim_tests = 0;
+    unsigned long long box_total = 0, prim_total = 0;
+
+    for (;;) {
+        __syncwarp();
+        if (alive && need && pix >= 0 && k == P.p.sample_count) {
+            float* dst = P.accum + 3ull * (unsigned long long)pix;
+            dst[0] = col.x; dst[1] = col.y; dst[2] = col.z;
+            pix = -1;
+        }
+        const bool want = alive && need && pix < 0;
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(&P.ctr[0], (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                const unsigned long long mine = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+                if (mine >= npix) alive = false;
+                else { pix = (int)mine; k = 0; col = mk3(0.f, 0.f, 0.f); }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+
+        if (alive && need) {  // PSC/main.cpp:305-308
+            const int s = P.p.sample_begin + k * P.p.sample_stride;
+            ++k;
+            g.begin(k0, k1, (uint32_t)pix, (uint32_t)s);
+            camera_ray(P.cam, nx, ny, pix % nx, pix / nx, g, r);
+            depth = 0;
+            L = mk3(0.f, 0.f, 0.f);
+            T = mk3(1.f, 1.f, 1.f);
+            need = false;
+        }
+        if (alive) {  // one level of color(), PSC/main.cpp:25-46, in iterative form
+            hit_t h;
+            medium_key mk;
+            mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)pix; mk.sample = g.sample; mk.depth = (uint32_t)depth;
+            closest_hit<COUNT>(P.S, r, P.p.t_min, P.p.t_max, narrow, mk, h, cnt);
+            ++n_rays;
+            if (COUNT) { box_total += cnt.box_tests; prim_total += cnt.prim_tests; cnt.box_tests = 0; cnt.prim_tests = 0; }
+            if (h.rec >= 0) {
+                surf_t s;
+                finish_hit(P.S, r, h, s);
+                if (emit) {
+                    const float4 m0 = __ldg(reinterpret_cast<const float4*>(P.S.materials + s.mat));
+                    if (__float_as_uint(m0.x) == RTNW_MAT_DIFFUSE_LIGHT)
+                        L = L + T * texture_value(P.S, __float_as_int(m0.y), s.u, s.v, s.p);
+                }
+                ray_t sc;
+                f3 att;
+                if (depth < P.p.max_depth && material_scatter(P.S, s.mat, r, s, g, att, sc)) {
+                    T = T * att;
+                    r = sc;
+                    ++depth;
+                } else {
+                    need = true;
+                }
+            } else {
+                if (sky) L = L + T * sky_color(r.d);
+                need = true;
+            }
+            if (need) {  // PSC/main.cpp:311-312
+                if (denan) {
+                    if (!(L.x == L.x)) L.x = 0.f;
+                    if (!(L.y == L.y)) L.y = 0.f;
+                    if (!(L.z == L.z)) L.z = 0.f;
+                }
+                col = col + L;
+            }
+        }
+    }
+    // work counters: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) n_rays += __shfl_xor_sync(0xffffffffu, n_rays, o);
+    if (lane == 0) atomicAdd(&P.ctr[1], n_rays);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            box_total += __shfl_xor_sync(0xffffffffu, box_total, o);
+            prim_total += __shfl_xor_sync(0xffffffffu, prim_total, o);
+        }
+        if (lane == 0) { atomicAdd(&P.ctr[2], box_total); atomicAdd(&P.ctr[3], prim_total); }
+    }
+}
+
+// one world->hit() per ray, PSC/main.cpp:27
+__global__ void __launch_bounds__(128) k_trace(const scene_view S, const rtnw_ray* __restrict__ rays, size_t n, float t_min,
+                                               float t_max, uint32_t flags, uint64_t seed, rtnw_hit* __restrict__ out) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const rtnw_ray in = rays[q];
+    ray_t r;
+    r.o = mk3(in.origin[0], in.origin[1], in.origin[2]);
+    r.d = mk3(in.direction[0], in.direction[1], in.direction[2]);
+    r.time = in.time;
+    medium_key mk;
+    mk.k0 = (uint32_t)seed; mk.k1 = (uint32_t)(seed >> 32); mk.pixel = in.key; mk.sample = 0; mk.depth = 0;
+    hit_t h;
+    trav_counters cnt;
+    closest_hit<false>(S, r, t_min, t_max, (flags & RTNW_F_CULL_NARROW) != 0, mk, h, cnt);
+    rtnw_hit o;
+    memset(&o, 0, sizeof o);
+    o.prim_id = -1;
+    o.mat_id = -1;
+    if (h.rec >= 0) {
+        surf_t s;
+        finish_hit(S, r, h, s);
+        o.prim_id = S.rec_leaf[h.rec];
+        o.sub_id = h.face;
+        o.t = h.t;
+        o.p[0] = s.p.x; o.p[1] = s.p.y; o.p[2] = s.p.z;
+        o.normal[0] = s.n.x; o.normal[1] = s.n.y; o.normal[2] = s.n.z;
+        o.u = s.u; o.v = s.v;
+        o.mat_id = s.mat;
+    }
+    out[q] = o;
+}
+
+__global__ void k_eval_texture(const scene_view S, int tex, const float* __restrict__ uvp, size_t n, float* __restrict__ rgb) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float* in = uvp + 5 * q;
+    const f3 c = texture_value(S, tex, in[0], in[1], mk3(in[2], in[3], in[4]));
+    rgb[3 * q] = c.x; rgb[3 * q + 1] = c.y; rgb[3 * q + 2] = c.z;
+}
+
+__global__ void k_eval_perlin(const scene_view S, int which, const float* __restrict__ xyz, size_t n, float* __restrict__ out) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const f3 p = mk3(xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2]);
+    out[q] = which == 0 ? perlin_noise(S, p) : perlin_turb(S, p);
+}
+
+__global__ void k_scatter(const scene_view S, const rtnw_ray* __restrict__ rays_in, const rtnw_hit* __restrict__ hits, size_t n,
+                          uint64_t seed, rtnw_ray* __restrict__ out_sc, float* __restrict__ out_att, float* __restrict__ out_em,
+                          int32_t* __restrict__ out_flag) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const rtnw_ray in = rays_in[q];
+    const rtnw_hit hh = hits[q];
+    ray_t r;
+    r.o = mk3(in.origin[0], in.origin[1], in.origin[2]);
+    r.d = mk3(in.direction[0], in.direction[1], in.direction[2]);
+    r.time = in.time;
+    surf_t s;
+    s.p = mk3(hh.p[0], hh.p[1], hh.p[2]);
+    s.n = mk3(hh.normal[0], hh.normal[1], hh.normal[2]);
+    s.u = hh.u; s.v = hh.v; s.mat = hh.mat_id;
+    rng_t g;
+    g.begin((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)q, 0u);
+    const f3 em = material_emitted(S, s.mat, s.u, s.v, s.p);
+    f3 att = mk3(0.f, 0.f, 0.f);
+    ray_t sc;
+    sc.o = att; sc.d = att; sc.time = 0.f;
+    const bool ok = material_scatter(S, s.mat, r, s, g, att, sc);
+    rtnw_ray o;
+    memset(&o, 0, sizeof o);
+    if (ok) {
+        o.origin[0] = sc.o.x; o.origin[1] = sc.o.y; o.origin[2] = sc.o.z;
+        o.direction[0] = sc.d.x; o.direction[1] = sc.d.y; o.direction[2] = sc.d.z;
+        o.time = sc.time;
+    } else {
+        att = mk3(0.f, 0.f, 0.f);
+    }
+    o.key = (uint32_t)q;
+    out_sc[q] = o;
+    out_att[3 * q] = att.x; out_att[3 * q + 1] = att.y; out_att[3 * q + 2] = att.z;
+    out_em[3 * q] = em.x; out_em[3 * q + 1] = em.y; out_em[3 * q + 2] = em.z;
+    out_flag[q] = ok ? 1 : 0;
+}
+
+__global__ void k_camera_rays(const rtnw_camera cam, int nx, int ny, const int32_t* __restrict__ ij, const int32_t* __restrict__ sample,
+                              size_t n, uint64_t seed, rtnw_ray* __restrict__ out) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int i = ij[2 * q], j = ij[2 * q + 1];
+    rng_t g;
+    g.begin((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(j * nx + i), (uint32_t)sample[q]);
+    ray_t r;
+    camera_ray(cam, nx, ny, i, j, g, r);
+    rtnw_ray o;
+    o.origin[0] = r.o.x; o.origin[1] = r.o.y; o.origin[2] = r.o.z;
+    o.direction[0] = r.d.x; o.direction[1] = r.d.y; o.direction[2] = r.d.z;
+    o.time = r.time;
+    o.key = (uint32_t)(j * nx + i);
+    out[q] = o;
+}
+
+// ================================================================================================ host side
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(RTNW_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+struct dev_buf {  // RAII device allocation for the query entry points
+    void* p = nullptr;
+    ~dev_buf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct rtnw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0, clock_khz = 0, smem_optin = 0, l2_bytes = 0;
+    float* accum = nullptr;          // device accumulation buffer of rtnw_render
+    size_t accum_floats = 0;
+    unsigned long long* ctr = nullptr;  // 4 device counters
+    int blocks_per_sm[2] = {0, 0};
+};
+
+struct rtnw_scene {
+    scene_view view;
+    void* slab = nullptr;  // one allocation holding every table
+    int32_t n_leaf_ids = 0;
+};
+
+namespace {
+
+// ---- scene_desc -> record stream -----------------------------------------------------------------------------
+struct stream_builder {
+    const rtnw_scene_desc& d;
+    std::vector<rec> recs;
+    std::vector<int32_t> leaf;
+    std::string err;
+    explicit stream_builder(const rtnw_scene_desc& desc) : d(desc) {}
+
+    static float bits(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+    static float ubits(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+    static int32_t as_int(float f) { int32_t v; std::memcpy(&v, &f, 4); return v; }
+
+    bool bad(const std::string& m) { if (err.empty()) err = m; return false; }
+
+    bool chain_ok(uint32_t chain) {
+        if (chain == 0) return true;
+        if (chain >= (uint32_t)d.n_xform_ops) return bad("transform chain index out of range");
+        const uint32_t n = d.xforms[chain].kind >> 8;
+        if (n == 0 || chain + n > (uint32_t)d.n_xform_ops) return bad("transform chain length out of range");
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t kk = d.xforms[chain + k].kind & 0xffu;
+            if (kk != RTNW_XF_TRANSLATE && kk != RTNW_XF_ROTATE_Y) return bad("unknown transform op");
+        }
+        return true;
+    }
+
+    void push(float4 a, float bx, float by, uint32_t tag, int32_t w, int32_t leaf_id) {
+        rec r;
+        r.a = a;
+        r.b = make_float4(bx, by, ubits(tag), bits(w));
+        recs.push_back(r);
+        leaf.push_back(leaf_id);
+    }
+
+    // Append the records of prim slots [first, first+count).  first_cont: narrowing flag of the first primitive;
+    // the following primitives of the range always continue its scope (list semantics).
+    bool emit_prims(int32_t first, int32_t count, bool first_cont, bool boundary) {
+        if (first < 0 || count < 0 || first + count > d.n_prim_slots) return bad("primitive range out of bounds");
+        bool cont = first_cont;
+        for (int32_t s = first; s < first + count; ++s) {
+            const rtnw_prim& p = d.prims[s];
+            const uint32_t kind = RTNW_KX_KIND(p.kx), flip = RTNW_KX_FLIP(p.kx), chain = RTNW_KX_XFORM(p.kx);
+            const int32_t id = (d.prim_ids && !boundary) ? d.prim_ids[s] : -1;
+            if (kind == RTNW_PRIM_EXT) return bad("stray continuation slot");
+            if (!chain_ok(chain)) return false;
+            if (chain >= (1u << 24)) return bad("transform chain index exceeds 24 bits");
+            if (!boundary && (p.mat < 0 || p.mat >= d.n_materials)) return bad("material index out of range");
+            switch (kind) {
+                case RTNW_PRIM_SPHERE:
+                    push(make_float4(p.f[0], p.f[1], p.f[2], p.f[3]), 0, 0, RTNW_TAG(K_SPHERE, flip, cont, chain), p.mat, id);
+                    break;
+                case RTNW_PRIM_MOVING_SPHERE: {
+                    if (s + 1 >= first + count || RTNW_KX_KIND(d.prims[s + 1].kx) != RTNW_PRIM_EXT)
+                        return bad("moving sphere without its continuation slot");
+                    const rtnw_prim& e = d.prims[s + 1];
+                    push(make_float4(p.f[0], p.f[1], p.f[2], p.f[3]), p.f[4], p.f[5], RTNW_TAG(K_MSPHERE, flip, cont, chain), p.mat, id);
+                    push(make_float4(e.f[0], e.f[1], e.f[2], 0), 0, 0, RTNW_TAG(K_EXT, 0, 1, 0), -1, id);
+                    ++s;
+                    break;
+                }
+                case RTNW_PRIM_RECT_XY:
+                case RTNW_PRIM_RECT_XZ:
+                case RTNW_PRIM_RECT_YZ: {
+                    const uint32_t k = kind == RTNW_PRIM_RECT_XY ? K_RECT_XY : (kind == RTNW_PRIM_RECT_XZ ? K_RECT_XZ : K_RECT_YZ);
+                    push(make_float4(p.f[0], p.f[1], p.f[2], p.f[3]), p.f[4], 0, RTNW_TAG(k, flip, cont, chain), p.mat, id);
+                    break;
+                }
+                case RTNW_PRIM_BOX:
+                    push(make_float4(p.f[0], p.f[1], p.f[2], p.f[3]), p.f[4], p.f[5], RTNW_TAG(K_BOX, flip, cont, chain), p.mat, id);
+                    break;
+                case RTNW_PRIM_MEDIUM: {
+                    if (boundary) return bad("constant_medium as the boundary of a constant_medium");
+                    const int32_t bfirst = as_int(p.f[1]), bcount = as_int(p.f[2]);
+                    const size_t at = recs.size();
+                    push(make_float4(p.f[0], p.f[3] /* leaf id bits */, 0, 0), 0, 0, RTNW_TAG(K_MEDIUM, flip, cont, chain), p.mat, id);
+                    if (!emit_prims(bfirst, bcount, true, true)) return false;
+                    recs[at].a.z = bits((int32_t)(recs.size() - at - 1));
+                    for (size_t q = at + 1; q < recs.size(); ++q) leaf[q] = id;
+                    break;
+                }
+                default: return bad("unknown primitive kind");
+            }
+            cont = true;
+        }
+        return true;
+    }
+
+    bool emit_child(int32_t ref, int32_t count, const float* bmin, const float* bmax, int depth) {
+        if (ref == RTNW_REF_NONE) return true;
+        if (ref >= 0) return emit_node(ref, bmin, bmax, depth + 1);
+        return emit_prims(~ref, count, false, false);
+    }
+
+    // bvh_node `idx` whose own box (stored in its parent, or in the item for the root) is [bmin,bmax]
+    bool emit_node(int32_t idx, const float* bmin, const float* bmax, int depth) {
+        if (idx < 0 || idx >= d.n_nodes) return bad("BVH node index out of range");
+        if (depth > 4096) return bad("BVH deeper than 4096 levels (cycle?)");
+        const rtnw_bvh_node& n = d.nodes[idx];
+        const size_t at = recs.size();
+        push(make_float4(bmin[0], bmin[1], bmin[2], bmax[0]), bmax[1], bmax[2], RTNW_TAG(K_NODE, 0, 0, 0), 0, -1);
+        if (!emit_child(n.left, n.lcount, n.lmin, n.lmax, depth)) return false;
+        if (!emit_child(n.right, n.rcount, n.rmin, n.rmax, depth)) return false;
+        recs[at].b.w = bits((int32_t)recs.size());  // skip link: first record after the subtree
+        return true;
+    }
+
+    bool run() {
+        if (d.abi_version != RTNW_ABI_VERSION) return bad("scene_desc.abi_version does not match this library");
+        if (d.n_items <= 0 || !d.items) return bad("scene has no items");
+        if (d.n_prim_slots < 0 || d.n_nodes < 0 || d.n_materials < 0 || d.n_textures < 0 || d.n_xform_ops < 1)
+            return bad("negative table size (or missing identity transform op 0)");
+        if ((d.n_prim_slots && !d.prims) || (d.n_nodes && !d.nodes) || (d.n_materials && !d.materials) ||
+            (d.n_textures && !d.textures) || !d.xforms)
+            return bad("null table pointer");
+        if (!d.perlin_ranvec || !d.perlin_perm_x || !d.perlin_perm_y || !d.perlin_perm_z) return bad("null perlin table");
+        for (int32_t t = 0; t < d.n_textures; ++t) {
+            const rtnw_texture& x = d.textures[t];
+            if (x.kind == RTNW_TEX_CHECKER) {
+                if (x.i0 <= t || x.i1 <= t || x.i0 >= d.n_textures || x.i1 >= d.n_textures)
+                    return bad("checker texture children must follow their parent in the table");
+            } else if (x.kind == RTNW_TEX_IMAGE) {
+                if (x.i0 < 0 || x.i1 <= 0 || x.i2 <= 0 || !d.images ||
+                    (uint64_t)x.i0 + 3ull * (uint64_t)x.i1 * (uint64_t)x.i2 > d.image_bytes)
+                    return bad("image texture outside the image pool");
+            } else if (x.kind != RTNW_TEX_CONSTANT && x.kind != RTNW_TEX_NOISE) {
+                return bad("unknown texture kind");
+            }
+        }
+        for (int32_t m = 0; m < d.n_materials; ++m) {
+            const rtnw_material& x = d.materials[m];
+            if (x.kind > RTNW_MAT_ISOTROPIC) return bad("unknown material kind");
+            const bool needs_tex = x.kind == RTNW_MAT_LAMBERTIAN || x.kind == RTNW_MAT_DIFFUSE_LIGHT || x.kind == RTNW_MAT_ISOTROPIC;
+            if (needs_tex && (x.tex < 0 || x.tex >= d.n_textures)) return bad("material texture index out of range");
+        }
+        for (int32_t i = 0; i < d.n_items; ++i) {
+            const rtnw_item& it = d.items[i];
+            if (!chain_ok(it.xform)) return false;
+            if (it.xform >= (1u << 24)) return bad("transform chain index exceeds 24 bits");
+            push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_ITEM, 0, 0, it.xform), (int32_t)it.kind, -1);
+            if (it.kind == RTNW_ITEM_PRIMS) {
+                if (!emit_prims(it.first, it.count, true, false)) return false;
+            } else if (it.kind == RTNW_ITEM_BVH) {
+                if (!emit_node(it.first, it.bmin, it.bmax, 0)) return false;
+            } else {
+                return bad("unknown item kind");
+            }
+        }
+        push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_END, 0, 0, 0), 0, -1);
+        return true;
+    }
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int check_ctx(rtnw_ctx* ctx) {
+    if (!ctx) return fail(RTNW_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return RTNW_OK;
+}
+
+template <bool COUNT>
+int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
+    int& bps = ctx->blocks_per_sm[COUNT ? 1 : 0];
+    if (bps == 0) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT>, RTNW_BLOCK, 0));
+        if (bps < 1) bps = 1;
+    }
+    int blocks = ctx->sm_count * bps;
+    const long long warps_needed = ((long long)a.p.nx * a.p.ny + 31) / 32;
+    const long long blocks_needed = (warps_needed * 32 + RTNW_BLOCK - 1) / RTNW_BLOCK;
+    if (blocks_needed < blocks) blocks = (int)blocks_needed;
+    if (const char* e = getenv("RTNW_GRID_BLOCKS")) { const int v = atoi(e); if (v > 0) blocks = v; }
+    k_render<COUNT><<<blocks, RTNW_BLOCK, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return RTNW_OK;
+}
+
+int validate_params(const rtnw_render_params* p) {
+    if (!p) return fail(RTNW_ERR_INVALID, "null render params");
+    if (p->nx <= 0 || p->ny <= 0 || (long long)p->nx * p->ny > 0x7fffffffLL / 4) return fail(RTNW_ERR_INVALID, "bad image size");
+    if (p->sample_count <= 0 || p->sample_stride <= 0 || p->sample_begin < 0) return fail(RTNW_ERR_INVALID, "bad sample range");
+    if (p->max_depth < 0) return fail(RTNW_ERR_INVALID, "bad max_depth");
+    if (p->background > RTNW_BG_SKY) return fail(RTNW_ERR_INVALID, "bad background");
+    return RTNW_OK;
+}
+
+// render into a device buffer on stream st; fills stats (kernel_ms from CUDA events on st)
+int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, const rtnw_render_params* p, float* accum_dev,
+                cudaStream_t st, rtnw_stats* stats) {
+    render_args a;
+    a.S = scene->view;
+    a.cam = *cam;
+    a.p = *p;
+    a.accum = accum_dev;
+    a.ctr = ctx->ctr;
+    CUDA_TRY(cudaMemsetAsync(ctx->ctr, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    const int rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true>(ctx, a, st) : launch_render<false>(ctx, a, st);
+    if (rc != RTNW_OK) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+    unsigned long long h[4];
+    CUDA_TRY(cudaMemcpyAsync(h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->paths = (uint64_t)p->nx * p->ny * p->sample_count;
+        stats->rays = h[1];
+        stats->box_tests = h[2];
+        stats->prim_tests = h[3];
+        CUDA_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev0, ctx->ev1));
+        stats->kernel_launches = 1;
+    }
+    return RTNW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtnw_last_error(void) { return g_err.c_str(); }
+int rtnw_abi_version(void) { return RTNW_ABI_VERSION; }
+
+int rtnw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int rtnw_ctx_create(int device, rtnw_ctx** out) {
+    if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(RTNW_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(RTNW_ERR_INVALID, "device index out of range");
+    int major = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(RTNW_ERR_CUDA, "device is not sm_100 (the library is built for sm_100a only)");
+    CUDA_TRY(cudaSetDevice(device));
+    rtnw_ctx* c = new rtnw_ctx();
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
+    cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&c->l2_bytes, cudaDevAttrL2CacheSize, device);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ctr, 4 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        rtnw_ctx_destroy(c);
+        return fail(RTNW_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return RTNW_OK;
+}
+
+int rtnw_ctx_destroy(rtnw_ctx* c) {
+    if (!c) return RTNW_OK;
+    cudaSetDevice(c->device);
+    if (c->accum) cudaFree(c->accum);
+    if (c->ctr) cudaFree(c->ctr);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RTNW_OK;
+}
+
+int rtnw_ctx_info(rtnw_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t* smem_optin, int32_t* l2_bytes) {
+    if (!ctx) return fail(RTNW_ERR_INVALID, "null context");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (clock_khz) *clock_khz = ctx->clock_khz;
+    if (smem_optin) *smem_optin = ctx->smem_optin;
+    if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+    return RTNW_OK;
+}
+
+int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out) {
+    if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (!desc) return fail(RTNW_ERR_INVALID, "null scene_desc");
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    stream_builder sb(*desc);
+    if (!sb.run()) return fail(RTNW_ERR_INVALID, "scene_desc: " + sb.err);
+
+    // perlin tables repacked for 128-bit gradient loads and byte permutations
+    std::vector<float4> ranvec(256);
+    std::vector<uint8_t> perm(768);
+    for (int i = 0; i < 256; ++i) {
+        ranvec[i] = make_float4(desc->perlin_ranvec[3 * i], desc->perlin_ranvec[3 * i + 1], desc->perlin_ranvec[3 * i + 2], 0.f);
+        const int32_t px = desc->perlin_perm_x[i], py = desc->perlin_perm_y[i], pz = desc->perlin_perm_z[i];
+        if ((px | py | pz) & ~255) return fail(RTNW_ERR_INVALID, "scene_desc: perlin permutation entry outside 0..255");
+        perm[i] = (uint8_t)px; perm[256 + i] = (uint8_t)py; perm[512 + i] = (uint8_t)pz;
+    }
+
+    // one slab, every table 256-byte aligned
+    const size_t sz_recs = sb.recs.size() * sizeof(rec), sz_leaf = sb.leaf.size() * sizeof(int32_t);
+    const size_t sz_xf = (size_t)desc->n_xform_ops * sizeof(rtnw_xform_op);
+    const size_t sz_mat = (size_t)desc->n_materials * sizeof(rtnw_material), sz_tex = (size_t)desc->n_textures * sizeof(rtnw_texture);
+    const size_t sz_img = (size_t)desc->image_bytes, sz_rv = 256 * sizeof(float4), sz_perm = 768;
+    size_t off = 0;
+    const size_t o_recs = off; off += align256(sz_recs);
+    const size_t o_leaf = off; off += align256(sz_leaf);
+    const size_t o_xf = off; off += align256(sz_xf);
+    const size_t o_mat = off; off += align256(sz_mat);
+    const size_t o_tex = off; off += align256(sz_tex);
+    const size_t o_rv = off; off += align256(sz_rv);
+    const size_t o_perm = off; off += align256(sz_perm);
+    const size_t o_img = off; off += align256(sz_img + 16);
+    std::vector<uint8_t> host(off, 0);
+    std::memcpy(host.data() + o_recs, sb.recs.data(), sz_recs);
+    std::memcpy(host.data() + o_leaf, sb.leaf.data(), sz_leaf);
+    std::memcpy(host.data() + o_xf, desc->xforms, sz_xf);
+    if (sz_mat) std::memcpy(host.data() + o_mat, desc->materials, sz_mat);
+    if (sz_tex) std::memcpy(host.data() + o_tex, desc->textures, sz_tex);
+    std::memcpy(host.data() + o_rv, ranvec.data(), sz_rv);
+    std::memcpy(host.data() + o_perm, perm.data(), sz_perm);
+    if (sz_img) std::memcpy(host.data() + o_img, desc->images, sz_img);
+
+    rtnw_scene* s = new rtnw_scene();
+    cudaError_t e = cudaMalloc(&s->slab, off);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->slab, host.data(), off, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (s->slab) cudaFree(s->slab);
+        delete s;
+        return fail(e == cudaErrorMemoryAllocation ? RTNW_ERR_NOMEM : RTNW_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    }
+    uint8_t* base = static_cast<uint8_t*>(s->slab);
+    s->view.recs = reinterpret_cast<const rec*>(base + o_recs);
+    s->view.rec_leaf = reinterpret_cast<const int32_t*>(base + o_leaf);
+    s->view.xforms = reinterpret_cast<const rtnw_xform_op*>(base + o_xf);
+    s->view.materials = reinterpret_cast<const rtnw_material*>(base + o_mat);
+    s->view.textures = reinterpret_cast<const rtnw_texture*>(base + o_tex);
+    s->view.ranvec = reinterpret_cast<const float4*>(base + o_rv);
+    s->view.perm = base + o_perm;
+    s->view.images = base + o_img;
+    s->view.n_recs = (int32_t)sb.recs.size();
+    s->view.n_materials = desc->n_materials;
+    s->view.n_textures = desc->n_textures;
+    *out = s;
+    return RTNW_OK;
+}
+
+int rtnw_scene_free(rtnw_ctx* ctx, rtnw_scene* scene) {
+    if (!scene) return RTNW_OK;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (scene->slab) cudaFree(scene->slab);
+    delete scene;
+    return RTNW_OK;
+}
+
+int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, const rtnw_render_params* params,
+                       float* accum_rgb_dev, void* cuda_stream, rtnw_stats* stats) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!scene || !cam || !accum_rgb_dev) return fail(RTNW_ERR_INVALID, "null argument");
+    if ((rc = validate_params(params)) != RTNW_OK) return rc;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return render_core(ctx, scene, cam, params, accum_rgb_dev, st, stats);
+}
+
+int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, const rtnw_render_params* params,
+                float* accum_rgb, rtnw_stats* stats) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!scene || !cam || !accum_rgb) return fail(RTNW_ERR_INVALID, "null argument");
+    if ((rc = validate_params(params)) != RTNW_OK) return rc;
+    const size_t floats = (size_t)params->nx * params->ny * 3;
+    if (ctx->accum_floats < floats) {
+        if (ctx->accum) cudaFree(ctx->accum);
+        ctx->accum = nullptr;
+        ctx->accum_floats = 0;
+        if (cudaMalloc(&ctx->accum, floats * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(RTNW_ERR_NOMEM, "cannot allocate the accumulation buffer");
+        }
+        ctx->accum_floats = floats;
+    }
+    cudaEvent_t t0, t1;
+    CUDA_TRY(cudaEventCreate(&t0));
+    CUDA_TRY(cudaEventCreate(&t1));
+    CUDA_TRY(cudaEventRecord(t0, ctx->stream));
+    rc = render_core(ctx, scene, cam, params, ctx->accum, ctx->stream, stats);
+    if (rc == RTNW_OK) {
+        cudaError_t e = cudaMemcpyAsync(accum_rgb, ctx->accum, floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(t1, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(RTNW_ERR_CUDA, std::string("result copy: ") + cudaGetErrorString(e));
+        else if (stats) cudaEventElapsedTime(&stats->total_ms, t0, t1);
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    return rc;
+}
+
+int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, size_t n, float t_min, float t_max, uint32_t flags,
+               uint64_t seed, rtnw_hit* out) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!scene || (n && (!rays || !out))) return fail(RTNW_ERR_INVALID, "null argument");
+    if (n == 0) return RTNW_OK;
+    dev_buf d_rays, d_out;
+    CUDA_TRY(d_rays.alloc(n * sizeof(rtnw_ray)));
+    CUDA_TRY(d_out.alloc(n * sizeof(rtnw_hit)));
+    CUDA_TRY(cudaMemcpyAsync(d_rays.p, rays, n * sizeof(rtnw_ray), cudaMemcpyHostToDevice, ctx->stream));
+    k_trace<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, flags, seed,
+                                                                  d_out.as<rtnw_hit>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n * sizeof(rtnw_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
+}
+
+int rtnw_eval_texture(rtnw_ctx* ctx, const rtnw_scene* scene, int32_t tex_id, const float* uvp, size_t n, float* rgb_out) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!scene || (n && (!uvp || !rgb_out))) return fail(RTNW_ERR_INVALID, "null argument");
+    if (tex_id < 0 || tex_id >= scene->view.n_textures) return fail(RTNW_ERR_INVALID, "texture index out of range");
+    if (n == 0) return RTNW_OK;
+    dev_buf d_in, d_out;
+    CUDA_TRY(d_in.alloc(n * 5 * sizeof(float)));
+    CUDA_TRY(d_out.alloc(n * 3 * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(d_in.p, uvp, n * 5 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_eval_texture<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(scene->view, tex_id, d_in.as<float>(), n, d_out.as<float>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, d_out.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
+}
+
+int rtnw_eval_perlin(rtnw_ctx* ctx, const rtnw_scene* scene, int32_t which, const float* xyz, size_t n, float* out) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!scene || (n && (!xyz || !out))) return fail(RTNW_ERR_INVALID, "null argument");
+    if (which != 0 && which != 1) return fail(RTNW_ERR_INVALID, "which must be 0 (noise) or 1 (turb)");
+    if (n == 0) return RTNW_OK;
+    dev_buf d_in, d_out;
+    CUDA_TRY(d_in.alloc(n * 3 * sizeof(float)));
+    CUDA_TRY(d_out.alloc(n * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(d_in.p, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_eval_perlin<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(scene->view, which, d_in.as<float>(), n, d_out.as<float>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
+}
+
+int rtnw_scatter(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays_in, const rtnw_hit* hits, size_t n, uint64_t seed,
+                 rtnw_ray* out_scattered, float* out_atten, float* out_emitted, int32_t* out_flag) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!scene || (n && (!rays_in || !hits || !out_scattered || !out_atten || !out_emitted || !out_flag)))
+        return fail(RTNW_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i)
+        if (hits[i].mat_id < 0 || hits[i].mat_id >= scene->view.n_materials) return fail(RTNW_ERR_INVALID, "hit.mat_id out of range");
+    if (n == 0) return RTNW_OK;
+    dev_buf d_rays, d_hits, d_sc, d_att, d_em, d_flag;
+    CUDA_TRY(d_rays.alloc(n * sizeof(rtnw_ray)));
+    CUDA_TRY(d_hits.alloc(n * sizeof(rtnw_hit)));
+    CUDA_TRY(d_sc.alloc(n * sizeof(rtnw_ray)));
+    CUDA_TRY(d_att.alloc(n * 3 * sizeof(float)));
+    CUDA_TRY(d_em.alloc(n * 3 * sizeof(float)));
+    CUDA_TRY(d_flag.alloc(n * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(d_rays.p, rays_in, n * sizeof(rtnw_ray), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_hits.p, hits, n * sizeof(rtnw_hit), cudaMemcpyHostToDevice, ctx->stream));
+    k_scatter<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), d_hits.as<rtnw_hit>(), n, seed,
+                                                                    d_sc.as<rtnw_ray>(), d_att.as<float>(), d_em.as<float>(),
+                                                                    d_flag.as<int32_t>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_scattered, d_sc.p, n * sizeof(rtnw_ray), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_atten, d_att.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_emitted, d_em.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_flag, d_flag.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
+}
+
+int rtnw_camera_rays(rtnw_ctx* ctx, const rtnw_camera* cam, int32_t nx, int32_t ny, const int32_t* ij, const int32_t* sample, size_t n,
+                     uint64_t seed, rtnw_ray* rays_out) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!cam || nx <= 0 || ny <= 0 || (n && (!ij || !sample || !rays_out))) return fail(RTNW_ERR_INVALID, "bad argument");
+    if (n == 0) return RTNW_OK;
+    dev_buf d_ij, d_s, d_out;
+    CUDA_TRY(d_ij.alloc(n * 2 * sizeof(int32_t)));
+    CUDA_TRY(d_s.alloc(n * sizeof(int32_t)));
+    CUDA_TRY(d_out.alloc(n * sizeof(rtnw_ray)));
+    CUDA_TRY(cudaMemcpyAsync(d_ij.p, ij, n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_s.p, sample, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_camera_rays<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(*cam, nx, ny, d_ij.as<int32_t>(), d_s.as<int32_t>(), n, seed,
+                                                                        d_out.as<rtnw_ray>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rays_out, d_out.p, n * sizeof(rtnw_ray), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
+}
+
+}  // extern "C"

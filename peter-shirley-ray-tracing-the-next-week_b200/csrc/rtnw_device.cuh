@@ -1,0 +1,606 @@
+// rtnw_device.cuh — device functions of the B200 path tracer (sm_100a).
+//
+// Everything the reference evaluates per ray on the CPU (PSC/ = "Peter-Shirley-Project Code/" of the reference):
+//   camera::get_ray                    PSC/camera.h:41-56
+//   hitable_list::hit / bvh_node::hit  PSC/hitable_list.h:20-32, PSC/bvh.h:29-54, PSC/aabb.h:33-49 (+F2 origin fix)
+//   sphere / moving_sphere / rects     PSC/sphere.h:25-52,92-118, PSC/aarect.h:50-100, PSC/box.h:36-38
+//   translate / rotate_y / flip        PSC/hitable.h:39-150
+//   constant_medium::hit               PSC/constant_medium.h:26-50
+//   material::scatter / emitted        PSC/material.h:16-151
+//   texture::value, perlin             PSC/texture.h, PSC/perlin.h, PSC/surface_texture.h
+//   color / de_nan / sample loop       PSC/main.cpp:25-46,232-242,304-313
+//
+// Numerical contract: float32 with the reference's operation order, no FMA contraction (the TU is compiled with
+// --fmad=false; IEEE div/sqrt are nvcc defaults), double only where the reference's C++ promotes to double.
+// Consequently t / p / normal are bit-identical to the reference for every primitive; only libm calls
+// (atan2f, asinf, sinf, log, pow) can differ by an ulp.
+//
+// Scene layout: ONE linear stream of 32-byte records, traversed front to back without a stack.
+// BVH nodes are stored in preorder with a skip link; because the reference's bvh_node::hit hands both children
+// the UN-narrowed [tmin,tmax] (PSC/bvh.h:34-35), the set of leaves it tests does not depend on traversal order,
+// and "closest hit, ties to the right child" equals "scan leaves left to right, replace unless best_t < t".
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "rtnw.h"
+
+namespace rtnw_dev {
+
+// ------------------------------------------------------------------------------------------------ records
+enum rec_kind : uint32_t {
+    K_SPHERE = 0, K_MSPHERE = 1, K_RECT_XY = 2, K_RECT_XZ = 3, K_RECT_YZ = 4, K_BOX = 5, K_MEDIUM = 6, K_EXT = 7,
+    K_NODE = 8, K_ITEM = 9, K_END = 10
+};
+#define RTNW_TAG_FLIP 16u
+#define RTNW_TAG_CONT 32u  // same narrowing scope as the previous primitive (list semantics, PSC/hitable_list.h:23-29)
+#define RTNW_TAG(kind, flip, cont, xf) ((uint32_t)(kind) | ((flip) ? RTNW_TAG_FLIP : 0u) | ((cont) ? RTNW_TAG_CONT : 0u) | ((uint32_t)(xf) << 8))
+
+struct __align__(16) rec {
+    float4 a;  // geometry
+    float4 b;  // b.x, b.y geometry; b.z = tag bits; b.w = int: material (prims) / skip index (nodes) / mode (items)
+};
+
+struct scene_view {
+    const rec* recs;            // the stream; recs[0] is the first ITEM, the last record is K_END
+    const int32_t* rec_leaf;    // per record: leaf id (parity output only)
+    const rtnw_xform_op* xforms;
+    const rtnw_material* materials;
+    const rtnw_texture* textures;
+    const uint8_t* images;
+    const float4* ranvec;       // 256 gradients, PSC/perlin.h:82-87
+    const uint8_t* perm;        // perm_x | perm_y | perm_z, 256 bytes each, PSC/perlin.h:99-106
+    int32_t n_recs, n_materials, n_textures;
+};
+
+// ------------------------------------------------------------------------------------------------ vec3
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ f3 operator*(float t, f3 a) { return mk3(t * a.x, t * a.y, t * a.z); }
+__device__ __forceinline__ f3 operator/(f3 a, float t) { return mk3(a.x / t, a.y / t, a.z / t); }  // PSC/vec3.h:82
+__device__ __forceinline__ f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // ((x+y)+z), PSC/vec3.h:90
+__device__ __forceinline__ float length(f3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ f3 unit_vector(f3 a) { return a / length(a); }
+
+struct ray_t { f3 o, d; float time; };
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+// Replaces the process-global drand48 stream.  The reference oracle (oracle/ref_harness.cpp) is
+// driven by the SAME generator, so GPU and reference consume identical numbers.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+struct rng_t {                 // sequential stream of one path: draw n = philox(n>>2, 0, sample, pixel)[n&3]
+    uint32_t k0, k1, pixel, sample, n;
+    uint32_t b0, b1, b2, b3;
+    __device__ __forceinline__ void begin(uint32_t key0, uint32_t key1, uint32_t px, uint32_t s) {
+        k0 = key0; k1 = key1; pixel = px; sample = s; n = 0;
+    }
+    __device__ __forceinline__ float draw() {
+        const uint32_t j = n & 3u;
+        if (j == 0) philox4x32_10(n >> 2, 0u, sample, pixel, k0, k1, b0, b1, b2, b3);
+        ++n;
+        return u01(j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : b3)));
+    }
+};
+// keyed draw of a medium's free-flight number: independent of traversal order and of how often the leaf is tested
+__device__ __forceinline__ float keyed_draw(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t leaf) {
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10(leaf, 1u + depth, sample, pixel, k0, k1, o0, o1, o2, o3);
+    return u01(o0);
+}
+
+// PSC/material.h:41-47.  g++ evaluates `vec3(drand48(),drand48(),drand48())` right to left: first draw -> z.
+__device__ __forceinline__ f3 random_in_unit_sphere(rng_t& g) {
+    f3 p;
+    do {
+        const float dz = g.draw(), dy = g.draw(), dx = g.draw();
+        p = 2.0f * mk3(dx, dy, dz) - mk3(1.f, 1.f, 1.f);
+    } while (dot(p, p) >= 1.0f);
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------ transforms
+// PSC/hitable.h:66-74 (translate) and :128-150 (rotate_y); chains are applied to the ray first-to-last.
+__device__ __forceinline__ void xform_ray(const rtnw_xform_op* __restrict__ ops, uint32_t chain, ray_t& r) {
+    if (chain == 0) return;
+    const uint32_t n = __ldg(&ops[chain].kind) >> 8;
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 op = __ldg(reinterpret_cast<const float4*>(ops + chain + k));
+        if ((__float_as_uint(op.w) & 0xffu) == RTNW_XF_TRANSLATE) {
+            r.o = r.o - mk3(op.x, op.y, op.z);
+        } else {  // ROTATE_Y: op.x = sin, op.y = cos
+            const float ox = op.y * r.o.x - op.x * r.o.z, oz = op.x * r.o.x + op.y * r.o.z;
+            const float dx = op.y * r.d.x - op.x * r.d.z, dz = op.x * r.d.x + op.y * r.d.z;
+            r.o.x = ox; r.o.z = oz; r.d.x = dx; r.d.z = dz;
+        }
+    }
+}
+// the hit is carried back out last-to-first
+__device__ __forceinline__ void xform_hit_back(const rtnw_xform_op* __restrict__ ops, uint32_t chain, f3& p, f3& nrm) {
+    if (chain == 0) return;
+    const uint32_t n = __ldg(&ops[chain].kind) >> 8;
+    for (int k = (int)n - 1; k >= 0; --k) {
+        const float4 op = __ldg(reinterpret_cast<const float4*>(ops + chain + k));
+        if ((__float_as_uint(op.w) & 0xffu) == RTNW_XF_TRANSLATE) {
+            p = p + mk3(op.x, op.y, op.z);
+        } else {
+            const float px = op.y * p.x + op.x * p.z, pz = (-op.x) * p.x + op.y * p.z;
+            const float nx = op.y * nrm.x + op.x * nrm.z, nz = (-op.x) * nrm.x + op.y * nrm.z;
+            p.x = px; p.z = pz; nrm.x = nx; nrm.z = nz;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ primitives
+// Each returns true and writes t when the reference's hit() would return true for (t_lo, t_hi).
+
+// PSC/sphere.h:25-52.  a = dot(d,d) is a pure function of the ray and is hoisted by the callers.
+__device__ __forceinline__ bool hit_sphere(f3 c, float radius, const ray_t& r, float a, float t_lo, float t_hi, float& t) {
+    const f3 oc = r.o - c;
+    const float b = dot(oc, r.d);
+    const float cc = dot(oc, oc) - radius * radius;
+    const float disc = b * b - a * cc;
+    if (disc > 0.f) {
+        const float sq = sqrtf(disc);
+        float temp = (-b - sq) / a;
+        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
+        temp = (-b + sq) / a;
+        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
+    }
+    return false;
+}
+// PSC/sphere.h:81-83
+__device__ __forceinline__ f3 moving_center(f3 c0, f3 c1, float time0, float time1, float time) {
+    return c0 + ((time - time0) / (time1 - time0)) * (c1 - c0);
+}
+// PSC/aarect.h:50-100: plane axis N, extent axes A,B; inclusive bounds; a NaN t passes, as in the reference.
+template <int N, int A, int B>
+__device__ __forceinline__ bool hit_rect(float a0, float a1, float b0, float b1, float k, const ray_t& r, float t_lo, float t_hi, float& t) {
+    const float* o = &r.o.x;
+    const float* d = &r.d.x;
+    const float tt = (k - o[N]) / d[N];
+    if (tt < t_lo || tt > t_hi) return false;
+    const float a = o[A] + tt * d[A];
+    const float b = o[B] + tt * d[B];
+    if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+    t = tt;
+    return true;
+}
+// PSC/box.h:23-38: inner list of six faces, order +z, -z, +y, -y, +x, -x, narrowing from t_hi.
+__device__ __forceinline__ bool hit_box(f3 p0, f3 p1, const ray_t& r, float t_lo, float t_hi, float& t, int& face) {
+    bool any = false;
+    float lim = t_hi, tt;
+    if (hit_rect<2, 0, 1>(p0.x, p1.x, p0.y, p1.y, p1.z, r, t_lo, lim, tt)) { any = true; lim = tt; face = 0; }
+    if (hit_rect<2, 0, 1>(p0.x, p1.x, p0.y, p1.y, p0.z, r, t_lo, lim, tt)) { any = true; lim = tt; face = 1; }
+    if (hit_rect<1, 0, 2>(p0.x, p1.x, p0.z, p1.z, p1.y, r, t_lo, lim, tt)) { any = true; lim = tt; face = 2; }
+    if (hit_rect<1, 0, 2>(p0.x, p1.x, p0.z, p1.z, p0.y, r, t_lo, lim, tt)) { any = true; lim = tt; face = 3; }
+    if (hit_rect<0, 1, 2>(p0.y, p1.y, p0.z, p1.z, p1.x, r, t_lo, lim, tt)) { any = true; lim = tt; face = 4; }
+    if (hit_rect<0, 1, 2>(p0.y, p1.y, p0.z, p1.z, p0.x, r, t_lo, lim, tt)) { any = true; lim = tt; face = 5; }
+    t = lim;
+    return any;
+}
+
+// One surface primitive record (not a medium) against a ray given in the enclosing frame.  `a_frame` is dot(d,d)
+// of that frame; a primitive with its own transform chain recomputes it from the transformed direction.
+__device__ __forceinline__ bool hit_surface(const scene_view& S, int i, float4 A, float4 B, uint32_t tag, const ray_t& r_frame,
+                                            float a_frame, float t_lo, float t_hi, float& t, int& face) {
+    const uint32_t kind = tag & 15u;
+    const uint32_t chain = tag >> 8;
+    ray_t r = r_frame;
+    float a = a_frame;
+    if (chain) {
+        xform_ray(S.xforms, chain, r);
+        a = dot(r.d, r.d);
+    }
+    face = 0;
+    switch (kind) {
+        case K_SPHERE: return hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_lo, t_hi, t);
+        case K_MSPHERE: {
+            const float4 A2 = __ldg(&S.recs[i + 1].a);
+            const f3 c = moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
+            return hit_sphere(c, A.w, r, a, t_lo, t_hi, t);
+        }
+        case K_RECT_XY: return hit_rect<2, 0, 1>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, t);
+        case K_RECT_XZ: return hit_rect<1, 0, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, t);
+        case K_RECT_YZ: return hit_rect<0, 1, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, t);
+        case K_BOX: return hit_box(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, t_lo, t_hi, t, face);
+        default: return false;
+    }
+}
+
+// boundary->hit(r, t_lo, t_hi, rec) of a constant_medium: list semantics over the nb boundary records that follow it
+__device__ __forceinline__ bool hit_boundary(const scene_view& S, int first, int nb, const ray_t& r, float a, float t_lo, float t_hi, float& t) {
+    bool any = false;
+    float lim = t_hi;
+    for (int i = first; i < first + nb; ++i) {
+        const float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
+        const uint32_t tag = __float_as_uint(B.z);
+        if ((tag & 15u) == K_EXT) continue;
+        float tt; int face;
+        if (hit_surface(S, i, A, B, tag, r, a, t_lo, lim, tt, face)) { any = true; lim = tt; }
+    }
+    t = lim;
+    return any;
+}
+
+struct medium_key { uint32_t k0, k1, pixel, sample, depth; };
+
+// PSC/constant_medium.h:26-50
+__device__ __forceinline__ bool hit_medium(const scene_view& S, int i, float4 A, uint32_t tag, const ray_t& r_frame, float a_frame,
+                                           float t_lo, float t_hi, const medium_key& mk, float& t) {
+    ray_t r = r_frame;
+    float a = a_frame;
+    const uint32_t chain = tag >> 8;
+    if (chain) { xform_ray(S.xforms, chain, r); a = dot(r.d, r.d); }
+    const int nb = __float_as_int(A.z);
+    float t1, t2;
+    if (!hit_boundary(S, i + 1, nb, r, a, -FLT_MAX, FLT_MAX, t1)) return false;
+    if (!hit_boundary(S, i + 1, nb, r, a, (float)((double)t1 + 0.0001), FLT_MAX, t2)) return false;
+    if (t1 < t_lo) t1 = t_lo;
+    if (t2 > t_hi) t2 = t_hi;
+    if (t1 >= t2) return false;
+    if (t1 < 0.f) t1 = 0.f;
+    const float len = sqrtf(a);  // r.direction().length(), same expression as dot(d,d)
+    const float inside = (t2 - t1) * len;
+    const float u = keyed_draw(mk.k0, mk.k1, mk.pixel, mk.sample, mk.depth, (uint32_t)__float_as_int(A.y));
+    const float hit_distance = (float)((double)(-(1.0f / A.x)) * log((double)u));
+    if (hit_distance < inside) {
+        t = t1 + hit_distance / len;
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------ closest hit
+struct hit_t {
+    float t;
+    int rec;      // record index, -1 = miss
+    int face;     // box face 0..5
+    uint32_t xf;  // transform chain of the item the record was reached in
+};
+
+struct trav_counters { uint32_t box_tests, prim_tests; };
+
+// world->hit(r, t_min, t_max, rec), PSC/main.cpp:27.  NARROW (RTNW_F_CULL_NARROW): node boxes are tested against
+// the current best t (with a relative margin) instead of the reference's un-narrowed range.
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit(const scene_view& S, const ray_t& wr, float t_min, float t_max, bool narrow,
+                                            const medium_key& mk, hit_t& h, trav_counters& cnt) {
+    float best_t = t_max;
+    int best = -1, best_face = 0;
+    uint32_t best_xf = 0, item_xf = 0;
+    float tmax0 = t_max, scope_lim = t_max;
+    ray_t r = wr;
+    f3 inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    float a = dot(r.d, r.d);
+    int i = 0;
+    for (;;) {
+        float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
+        uint32_t tag = __float_as_uint(B.z);
+        // ---- node phase: chase boxes until this lane stands on something else
+        while ((tag & 15u) == K_NODE) {
+            if (COUNT) cnt.box_tests++;
+            // PSC/aabb.h:33-49 with r.origin() (F2): selecting the near/far plane by the sign of invD first is the
+            // reference's swap of (t0,t1) afterwards
+            const float hi = narrow ? best_t + fabsf(best_t) * 1e-4f : tmax0;
+            float lo_t = t_min, hi_t = hi;
+            {
+                const bool neg = inv.x < 0.0f;
+                const float t0 = ((neg ? A.w : A.x) - r.o.x) * inv.x, t1 = ((neg ? A.x : A.w) - r.o.x) * inv.x;
+                lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+            }
+            {
+                const bool neg = inv.y < 0.0f;
+                const float t0 = ((neg ? B.x : A.y) - r.o.y) * inv.y, t1 = ((neg ? A.y : B.x) - r.o.y) * inv.y;
+                lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+            }
+            {
+                const bool neg = inv.z < 0.0f;
+                const float t0 = ((neg ? B.y : A.z) - r.o.z) * inv.z, t1 = ((neg ? A.z : B.y) - r.o.z) * inv.z;
+                lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+            }
+            i = (hi_t <= lo_t) ? __float_as_int(B.w) : i + 1;
+            A = __ldg(&S.recs[i].a); B = __ldg(&S.recs[i].b);
+            tag = __float_as_uint(B.z);
+        }
+        const uint32_t kind = tag & 15u;
+        if (kind == K_END) break;
+        if (kind == K_ITEM) {
+            // next element of the top-level hitable_list: it sees t_max = closest_so_far (PSC/hitable_list.h:25)
+            item_xf = tag >> 8;
+            r = wr;
+            xform_ray(S.xforms, item_xf, r);
+            inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+            a = dot(r.d, r.d);
+            tmax0 = best_t;
+            scope_lim = best_t;
+            ++i;
+            continue;
+        }
+        // ---- primitive phase
+        if (COUNT) cnt.prim_tests++;
+        const float lim = (tag & RTNW_TAG_CONT) ? scope_lim : tmax0;
+        float t; int face = 0; bool hit;
+        int step = 1;
+        if (kind == K_MEDIUM) {
+            hit = hit_medium(S, i, A, tag, r, a, t_min, lim, mk, t);
+            step = 1 + __float_as_int(A.z);
+        } else {
+            hit = hit_surface(S, i, A, B, tag, r, a, t_min, lim, t, face);
+            if (kind == K_MSPHERE) step = 2;
+        }
+        if (hit) {
+            scope_lim = t;
+            if (!(best_t < t)) { best_t = t; best = i; best_face = face; best_xf = item_xf; }
+        }
+        i += step;
+    }
+    h.t = best_t; h.rec = best; h.face = best_face; h.xf = best_xf;
+}
+
+// PSC/hitable.h:14-19
+__device__ __forceinline__ void get_sphere_uv(f3 p, float& u, float& v) {
+    const float phi = atan2f(p.z, p.x);
+    const float theta = asinf(p.y);
+    u = (float)(1.0 - ((double)phi + M_PI) / (2.0 * M_PI));
+    v = (float)(((double)theta + M_PI / 2.0) / M_PI);
+}
+
+struct surf_t { f3 p, n; float u, v; int mat; };
+
+// Rebuild the hit_record of the winning record: p / normal / uv are pure functions of (ray, primitive, t), so the
+// traversal only tracks (t, record) and the record is evaluated once here.
+__device__ __forceinline__ void finish_hit(const scene_view& S, const ray_t& wr, const hit_t& h, surf_t& s) {
+    const float4 A = __ldg(&S.recs[h.rec].a), B = __ldg(&S.recs[h.rec].b);
+    const uint32_t tag = __float_as_uint(B.z);
+    const uint32_t kind = tag & 15u, chain = tag >> 8;
+    ray_t r = wr;
+    xform_ray(S.xforms, h.xf, r);
+    xform_ray(S.xforms, chain, r);
+    const float t = h.t;
+    s.p = r.o + t * r.d;  // ray::point_at_parameter, PSC/ray.h:18
+    s.u = 0.f; s.v = 0.f;  // the reference leaves u,v unwritten for moving spheres and media
+    s.mat = __float_as_int(B.w);
+    bool flip = (tag & RTNW_TAG_FLIP) != 0;
+    switch (kind) {
+        case K_SPHERE: {
+            s.n = (s.p - mk3(A.x, A.y, A.z)) / A.w;
+            get_sphere_uv(s.n, s.u, s.v);
+            break;
+        }
+        case K_MSPHERE: {
+            const float4 A2 = __ldg(&S.recs[h.rec + 1].a);
+            const f3 c = moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
+            s.n = (s.p - c) / A.w;
+            break;
+        }
+        case K_RECT_XY: s.u = (s.p.x - A.x) / (A.y - A.x); s.v = (s.p.y - A.z) / (A.w - A.z); s.n = mk3(0, 0, 1); break;
+        case K_RECT_XZ: s.u = (s.p.x - A.x) / (A.y - A.x); s.v = (s.p.z - A.z) / (A.w - A.z); s.n = mk3(0, 1, 0); break;
+        case K_RECT_YZ: s.u = (s.p.y - A.x) / (A.y - A.x); s.v = (s.p.z - A.z) / (A.w - A.z); s.n = mk3(1, 0, 0); break;
+        case K_BOX: {
+            const f3 p0 = mk3(A.x, A.y, A.z), p1 = mk3(A.w, B.x, B.y);
+            const int axis = h.face >> 1;  // 0: xy faces, 1: xz faces, 2: yz faces
+            if (axis == 0) { s.u = (s.p.x - p0.x) / (p1.x - p0.x); s.v = (s.p.y - p0.y) / (p1.y - p0.y); s.n = mk3(0, 0, 1); }
+            else if (axis == 1) { s.u = (s.p.x - p0.x) / (p1.x - p0.x); s.v = (s.p.z - p0.z) / (p1.z - p0.z); s.n = mk3(0, 1, 0); }
+            else { s.u = (s.p.y - p0.y) / (p1.y - p0.y); s.v = (s.p.z - p0.z) / (p1.z - p0.z); s.n = mk3(1, 0, 0); }
+            if (h.face & 1) flip = !flip;  // faces 1,3,5 are flip_normals(rect), PSC/box.h:29-33
+            break;
+        }
+        default: s.n = mk3(1, 0, 0); break;  // K_MEDIUM: "arbitrary", PSC/constant_medium.h:44
+    }
+    if (flip) s.n = -s.n;
+    xform_hit_back(S.xforms, chain, s.p, s.n);
+    xform_hit_back(S.xforms, h.xf, s.p, s.n);
+}
+
+// ------------------------------------------------------------------------------------------------ textures
+// PSC/perlin.h:25-61.  noise() smooths u,v,w and perlin_interp smooths them again (and uses the smoothed u in
+// weight_v) — reproduced as written.
+__device__ __forceinline__ float perlin_noise(const scene_view& S, f3 p) {
+    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    u = u * u * (3.f - 2.f * u);
+    v = v * v * (3.f - 2.f * v);
+    w = w * w * (3.f - 2.f * w);
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    const float uu = u * u * (3.f - 2.f * u);
+    const float vv = v * v * (3.f - 2.f * v);
+    const float ww = w * w * (3.f - 2.f * w);
+    uint32_t hx[2], hy[2], hz[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        hx[d] = __ldg(&S.perm[(i + d) & 255]);
+        hy[d] = __ldg(&S.perm[256 + ((j + d) & 255)]);
+        hz[d] = __ldg(&S.perm[512 + ((k + d) & 255)]);
+    }
+    float accum = 0.f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const float4 c = __ldg(&S.ranvec[hx[di] ^ hy[dj] ^ hz[dk]]);
+                const f3 weight_v = mk3(u - (float)di, v - (float)dj, w - (float)dk);
+                accum += ((float)di * uu + (float)(1 - di) * (1.f - uu)) *
+                         ((float)dj * vv + (float)(1 - dj) * (1.f - vv)) *
+                         ((float)dk * ww + (float)(1 - dk) * (1.f - ww)) * dot(mk3(c.x, c.y, c.z), weight_v);
+            }
+    return accum;
+}
+// PSC/perlin.h:64-74
+__device__ __forceinline__ float perlin_turb(const scene_view& S, f3 p) {
+    float accum = 0.f, weight = 1.0f;
+    f3 q = p;
+    for (int o = 0; o < 7; ++o) {
+        accum += weight * perlin_noise(S, q);
+        weight *= 0.5f;
+        q = 2.f * q;
+    }
+    return fabsf(accum);
+}
+
+// texture::value(u, v, p): PSC/texture.h:22-56, PSC/surface_texture.h:19-30
+__device__ __forceinline__ f3 texture_value(const scene_view& S, int tex, float u, float v, f3 p) {
+    for (;;) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(S.textures + tex));      // kind, i0, i1, i2
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(S.textures + tex) + 1);  // c[3], pad
+        const uint32_t kind = __float_as_uint(t0.x);
+        if (kind == RTNW_TEX_CONSTANT) return mk3(t1.x, t1.y, t1.z);
+        if (kind == RTNW_TEX_CHECKER) {
+            const float sines = sinf(10.f * p.x) * sinf(10.f * p.y) * sinf(10.f * p.z);
+            tex = sines < 0.f ? __float_as_int(t0.z) /* odd */ : __float_as_int(t0.y) /* even */;
+            continue;
+        }
+        if (kind == RTNW_TEX_NOISE) {
+            const float scale = t1.x;
+            const float s = 1.f + sinf(scale * p.x + 5.f * perlin_turb(S, scale * p));
+            return mk3(0.5f * s, 0.5f * s, 0.5f * s);  // vec3(1,1,1)*0.5 = (0.5,0.5,0.5) exactly, then * s
+        }
+        // image: nearest texel, flipped u and v
+        const int off = __float_as_int(t0.y), nx = __float_as_int(t0.z), ny = __float_as_int(t0.w);
+        int i = (int)((1.f - u) * (float)nx);
+        int j = (int)((double)((1.f - v) * (float)ny) - 0.001);
+        if (i < 0) i = 0;
+        if (j < 0) j = 0;
+        if (i > nx - 1) i = nx - 1;
+        if (j > ny - 1) j = ny - 1;
+        const uint8_t* px = S.images + off + 3 * i + 3 * nx * j;
+        return mk3((float)__ldg(px) / 255.0f, (float)__ldg(px + 1) / 255.0f, (float)__ldg(px + 2) / 255.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ materials
+// PSC/material.h:16-20: float r0; the return expression is evaluated in double (pow(float,int) promotes)
+__device__ __forceinline__ float schlick(float cosine, float ref_idx) {
+    float r0 = (1.f - ref_idx) / (1.f + ref_idx);
+    r0 = r0 * r0;
+    const double x = (double)(1.f - cosine);
+    const double x2 = x * x;
+    return (float)((double)r0 + (double)(1.f - r0) * (x2 * x2 * x));
+}
+// PSC/material.h:23-33
+__device__ __forceinline__ bool refract(f3 v, f3 n, float ni_over_nt, f3& refracted) {
+    const f3 uv = unit_vector(v);
+    const float dt = dot(uv, n);
+    const float disc = 1.0f - ni_over_nt * ni_over_nt * (1.f - dt * dt);
+    if (disc > 0.f) {
+        refracted = ni_over_nt * (uv - dt * n) - sqrtf(disc) * n;
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ f3 reflect(f3 v, f3 n) { return v - (2.f * dot(v, n)) * n; }  // PSC/material.h:36-38
+
+// material::emitted(u,v,p), PSC/material.h:56-57,134-136
+__device__ __forceinline__ f3 material_emitted(const scene_view& S, int mat, float u, float v, f3 p) {
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(S.materials + mat));
+    if (__float_as_uint(m0.x) != RTNW_MAT_DIFFUSE_LIGHT) return mk3(0.f, 0.f, 0.f);
+    return texture_value(S, __float_as_int(m0.y), u, v, p);
+}
+// material::scatter(r_in, rec, attenuation, scattered), PSC/material.h:64-149
+__device__ __forceinline__ bool material_scatter(const scene_view& S, int mat, const ray_t& r_in, const surf_t& s, rng_t& g,
+                                                 f3& attenuation, ray_t& scattered) {
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(S.materials + mat));      // kind, tex, f, pad
+    const uint32_t kind = __float_as_uint(m0.x);
+    switch (kind) {
+        case RTNW_MAT_LAMBERTIAN: {
+            const f3 target = s.p + s.n + random_in_unit_sphere(g);
+            scattered.o = s.p; scattered.d = target - s.p; scattered.time = r_in.time;
+            attenuation = texture_value(S, __float_as_int(m0.y), s.u, s.v, s.p);
+            return true;
+        }
+        case RTNW_MAT_METAL: {
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(S.materials + mat) + 1);  // albedo
+            const f3 reflected = reflect(unit_vector(r_in.d), s.n);
+            scattered.o = s.p; scattered.d = reflected + m0.z * random_in_unit_sphere(g); scattered.time = 0.f;
+            attenuation = mk3(m1.x, m1.y, m1.z);
+            return dot(scattered.d, s.n) > 0.f;
+        }
+        case RTNW_MAT_DIELECTRIC: {
+            const float ref_idx = m0.z;
+            f3 outward_normal;
+            const f3 reflected = reflect(r_in.d, s.n);
+            float ni_over_nt, reflect_prob, cosine;
+            attenuation = mk3(1.f, 1.f, 1.f);
+            f3 refracted = mk3(0.f, 0.f, 0.f);
+            const float dn = dot(r_in.d, s.n);
+            if (dn > 0.f) {
+                outward_normal = -s.n;
+                ni_over_nt = ref_idx;
+                cosine = dn / length(r_in.d);
+                cosine = sqrtf(1.f - ref_idx * ref_idx * (1.f - cosine * cosine));
+            } else {
+                outward_normal = s.n;
+                ni_over_nt = 1.0f / ref_idx;
+                cosine = -dn / length(r_in.d);
+            }
+            if (refract(r_in.d, outward_normal, ni_over_nt, refracted)) reflect_prob = schlick(cosine, ref_idx);
+            else reflect_prob = 1.0f;
+            scattered.o = s.p; scattered.time = 0.f;
+            scattered.d = (g.draw() < reflect_prob) ? reflected : refracted;
+            return true;
+        }
+        case RTNW_MAT_ISOTROPIC: {
+            scattered.o = s.p; scattered.d = random_in_unit_sphere(g); scattered.time = 0.f;
+            attenuation = texture_value(S, __float_as_int(m0.y), s.u, s.v, s.p);
+            return true;
+        }
+        default: return false;  // diffuse_light
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ camera
+// PSC/main.cpp:305-306 + PSC/camera.h:41-56.  Draw order of the path's sequential stream: jitter u, jitter v,
+// disk (first draw -> y, second -> x, g++ right-to-left), time.
+__device__ __forceinline__ void camera_ray(const rtnw_camera& c, int nx, int ny, int i, int j, rng_t& g, ray_t& r) {
+    const float s = ((float)i + g.draw()) / (float)nx;  // float(i + drand48()): the double sum is exact, one rounding
+    const float t = ((float)j + g.draw()) / (float)ny;
+    float px, py;
+    do {
+        const float dy = g.draw(), dx = g.draw();
+        px = 2.0f * dx - 1.f; py = 2.0f * dy - 1.f;
+    } while (px * px + py * py + 0.f >= 1.0f);
+    const float rdx = c.lens_radius * px, rdy = c.lens_radius * py;
+    const f3 cu = mk3(c.u[0], c.u[1], c.u[2]), cv = mk3(c.v[0], c.v[1], c.v[2]);
+    const f3 offset = rdx * cu + rdy * cv;
+    const float time = (float)((double)c.time0 + (double)g.draw() * (double)(c.time1 - c.time0));
+    const f3 org = mk3(c.origin[0], c.origin[1], c.origin[2]);
+    const f3 llc = mk3(c.lower_left_corner[0], c.lower_left_corner[1], c.lower_left_corner[2]);
+    const f3 hor = mk3(c.horizontal[0], c.horizontal[1], c.horizontal[2]);
+    const f3 ver = mk3(c.vertical[0], c.vertical[1], c.vertical[2]);
+    r.o = org + offset;
+    r.d = llc + s * hor + t * ver - org - offset;
+    r.time = time;
+}
+
+// TNW/Chapter01_Motion Blur.cpp:29-31
+__device__ __forceinline__ f3 sky_color(f3 d) {
+    const f3 ud = unit_vector(d);
+    const float t = 0.5f * (ud.y + 1.0f);
+    return (1.0f - t) * mk3(1.f, 1.f, 1.f) + t * mk3(0.5f, 0.7f, 1.0f);
+}
+
+}  // namespace rtnw_dev
