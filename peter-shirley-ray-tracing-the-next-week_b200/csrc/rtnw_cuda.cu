@@ -28,18 +28,28 @@ struct render_args {
     unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests
 };
 
-// One thread = one pixel at a time: its samples are traced back to back and summed in sample order, exactly like
-// `col += temp` in PSC/main.cpp:304-313, so a pixel's sum does not depend on scheduling.  Threads are persistent:
-// a lane that finishes its pixel pulls the next one from a global counter (warp-aggregated), so a warp stays full
-// until the image is exhausted; a lane whose path ends starts the next sample of its pixel in the same iteration
-// of the warp loop (path regeneration), which absorbs the 51-bounce tail.
+typedef coop_smem<RTNW_BLOCK> block_smem;
+
+// The sample loop of PSC/main.cpp:299-313 as ONE persistent megakernel.
+//
+// One thread owns one pixel at a time: its samples are traced back to back and summed in sample order, exactly like
+// `col += temp` in the reference, so a pixel's sum never depends on scheduling (no atomics on the image).  A thread
+// that finishes its pixel pulls the next one from a global counter (warp-aggregated atomic); a thread whose path ends
+// starts the next sample of its pixel in the same round (path regeneration, which absorbs the 51-bounce tail).
+//
+// The block advances in rounds, one ray per thread per round: regenerate -> closest hit -> shade.  The closest hit is
+// block-cooperative (coop_closest_hit): list items in lockstep, BVH items as uniform tasks from shared-memory queues.
+// A per-lane traversal state machine was measured at 2-13 active lanes of 32 per instruction (profiles/r1-r3*.txt);
+// this form keeps every phase uniform across the warp.
 template <bool COUNT>
 __global__ void __launch_bounds__(RTNW_BLOCK) k_render(const render_args P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    block_smem& sm = *reinterpret_cast<block_smem*>(smem_raw);
+    constexpr unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int nx = P.p.nx, ny = P.p.ny;
     const unsigned long long npix = (unsigned long long)nx * (unsigned long long)ny;
     const uint32_t k0 = (uint32_t)P.p.seed, k1 = (uint32_t)(P.p.seed >> 32);
-    const bool narrow = (P.p.flags & RTNW_F_CULL_NARROW) != 0;
     const bool emit = (P.p.flags & RTNW_F_EMIT) != 0;
     const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
     const bool sky = P.p.background == RTNW_BG_SKY;
@@ -47,76 +57,75 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_render(const render_args P) {
     bool alive = true, need = true;
     int pix = -1, k = 0, depth = 0;
     f3 col = mk3(0.f, 0.f, 0.f), L = col, T = col;
-    ray_t r;
-    r.o = col; r.d = col; r.time = 0.f;
+    ray_t wr;
+    wr.o = col; wr.d = mk3(1.f, 1.f, 1.f); wr.time = 0.f;
     rng_t g;
     g.begin(k0, k1, 0, 0);
-    unsigned long long n_rays = 0;
+    unsigned long long n_rays = 0, box_total = 0, prim_total = 0;
     trav_counters cnt;
     cnt.box_tests = 0; cnt.prim_tests = 0;
-    unsigned long long box_total = 0, prim_total = 0;
 
     for (;;) {
-        __syncwarp();
+        // ---- next sample of the pixel, or next pixel, PSC/main.cpp:299-308
         if (alive && need && pix >= 0 && k == P.p.sample_count) {
             float* dst = P.accum + 3ull * (unsigned long long)pix;
             dst[0] = col.x; dst[1] = col.y; dst[2] = col.z;
             pix = -1;
         }
         const bool want = alive && need && pix < 0;
-        const unsigned m = __ballot_sync(0xffffffffu, want);
+        const unsigned m = __ballot_sync(FULL, want);
         if (m) {
             const int leader = __ffs(m) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(&P.ctr[0], (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
+            base = __shfl_sync(FULL, base, leader);
             if (want) {
                 const unsigned long long mine = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
                 if (mine >= npix) alive = false;
                 else { pix = (int)mine; k = 0; col = mk3(0.f, 0.f, 0.f); }
             }
         }
-        if (!__any_sync(0xffffffffu, alive)) break;
-
-        if (alive && need) {  // PSC/main.cpp:305-308
+        if (__syncthreads_count(alive) == 0) break;
+        if (alive && need) {
             const int s = P.p.sample_begin + k * P.p.sample_stride;
             ++k;
             g.begin(k0, k1, (uint32_t)pix, (uint32_t)s);
-            camera_ray(P.cam, nx, ny, pix % nx, pix / nx, g, r);
+            camera_ray(P.cam, nx, ny, pix % nx, pix / nx, g, wr);
             depth = 0;
             L = mk3(0.f, 0.f, 0.f);
             T = mk3(1.f, 1.f, 1.f);
             need = false;
         }
-        if (alive) {  // one level of color(), PSC/main.cpp:25-46, in iterative form
-            hit_t h;
-            medium_key mk;
-            mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)pix; mk.sample = g.sample; mk.depth = (uint32_t)depth;
-            closest_hit<COUNT>(P.S, r, P.p.t_min, P.p.t_max, narrow, mk, h, cnt);
+        // ---- world->hit(r, t_min, t_max, rec), PSC/main.cpp:27
+        medium_key mk;
+        mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)pix; mk.sample = g.sample; mk.depth = (uint32_t)depth;
+        const hkey_t key = coop_closest_hit<RTNW_BLOCK, COUNT>(P.S, sm, wr, alive, P.p.t_min, P.p.t_max, mk, cnt);
+        // ---- one level of color(), PSC/main.cpp:25-46, in iterative form
+        if (alive) {
             ++n_rays;
-            if (COUNT) { box_total += cnt.box_tests; prim_total += cnt.prim_tests; cnt.box_tests = 0; cnt.prim_tests = 0; }
+            hit_t h;
+            key_to_hit(P.S, key, P.p.t_max, h);
+            need = true;
             if (h.rec >= 0) {
                 surf_t s;
-                finish_hit(P.S, r, h, s);
-                if (emit) {
-                    const float4 m0 = __ldg(reinterpret_cast<const float4*>(P.S.materials + s.mat));
-                    if (__float_as_uint(m0.x) == RTNW_MAT_DIFFUSE_LIGHT)
-                        L = L + T * texture_value(P.S, __float_as_int(m0.y), s.u, s.v, s.p);
+                finish_hit(P.S, wr, h, s);
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(P.S.materials + s.mat));
+                if (__float_as_uint(m0.x) == RTNW_MAT_DIFFUSE_LIGHT) {  // the only material that emits; it never scatters
+                    if (emit) L = L + T * texture_value(P.S, __float_as_int(m0.y), s.u, s.v, s.p);
+                } else if (depth < P.p.max_depth) {
+                    ray_t sc;
+                    f3 att;
+                    if (material_scatter(P.S, s.mat, wr, s, g, att, sc)) {
+                        T = T * att;
+                        wr = sc;
+                        ++depth;
+                        need = false;
+                    }
                 }
-                ray_t sc;
-                f3 att;
-                if (depth < P.p.max_depth && material_scatter(P.S, s.mat, r, s, g, att, sc)) {
-                    T = T * att;
-                    r = sc;
-                    ++depth;
-                } else {
-                    need = true;
-                }
-            } else {
-                if (sky) L = L + T * sky_color(r.d);
-                need = true;
+            } else if (sky) {
+                L = L + T * sky_color(wr.d);
             }
-            if (need) {  // PSC/main.cpp:311-312
+            if (need) {  // the path ended: PSC/main.cpp:311-312
                 if (denan) {
                     if (!(L.x == L.x)) L.x = 0.f;
                     if (!(L.y == L.y)) L.y = 0.f;
@@ -127,32 +136,41 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_render(const render_args P) {
         }
     }
     // work counters: one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) n_rays += __shfl_xor_sync(0xffffffffu, n_rays, o);
+    if (COUNT) { box_total = cnt.box_tests; prim_total = cnt.prim_tests; }
+    for (int o = 16; o > 0; o >>= 1) n_rays += __shfl_xor_sync(FULL, n_rays, o);
     if (lane == 0) atomicAdd(&P.ctr[1], n_rays);
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {
-            box_total += __shfl_xor_sync(0xffffffffu, box_total, o);
-            prim_total += __shfl_xor_sync(0xffffffffu, prim_total, o);
+            box_total += __shfl_xor_sync(FULL, box_total, o);
+            prim_total += __shfl_xor_sync(FULL, prim_total, o);
         }
         if (lane == 0) { atomicAdd(&P.ctr[2], box_total); atomicAdd(&P.ctr[3], prim_total); }
     }
 }
 
-// one world->hit() per ray, PSC/main.cpp:27
-__global__ void __launch_bounds__(128) k_trace(const scene_view S, const rtnw_ray* __restrict__ rays, size_t n, float t_min,
-                                               float t_max, uint32_t flags, uint64_t seed, rtnw_hit* __restrict__ out) {
+// one world->hit() per ray, PSC/main.cpp:27 — the same block-cooperative closest hit the renderer uses
+__global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const rtnw_ray* __restrict__ rays, size_t n, float t_min,
+                                                      float t_max, uint64_t seed, rtnw_hit* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    block_smem& sm = *reinterpret_cast<block_smem*>(smem_raw);
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const rtnw_ray in = rays[q];
+    const bool active = q < n;  // idle threads of the last block still work on the block's BVH tasks
+    rtnw_ray in;
+    memset(&in, 0, sizeof in);
+    in.direction[0] = 1.f;
+    if (active) in = rays[q];
     ray_t r;
     r.o = mk3(in.origin[0], in.origin[1], in.origin[2]);
     r.d = mk3(in.direction[0], in.direction[1], in.direction[2]);
     r.time = in.time;
     medium_key mk;
     mk.k0 = (uint32_t)seed; mk.k1 = (uint32_t)(seed >> 32); mk.pixel = in.key; mk.sample = 0; mk.depth = 0;
-    hit_t h;
     trav_counters cnt;
-    closest_hit<false>(S, r, t_min, t_max, (flags & RTNW_F_CULL_NARROW) != 0, mk, h, cnt);
+    cnt.box_tests = 0; cnt.prim_tests = 0;
+    const hkey_t key = coop_closest_hit<RTNW_BLOCK, false>(S, sm, r, active, t_min, t_max, mk, cnt);
+    if (!active) return;
+    hit_t h;
+    key_to_hit(S, key, t_max, h);
     rtnw_hit o;
     memset(&o, 0, sizeof o);
     o.prim_id = -1;
@@ -289,6 +307,8 @@ struct stream_builder {
     const rtnw_scene_desc& d;
     std::vector<rec> recs;
     std::vector<int32_t> leaf;
+    std::vector<uint32_t> rec_xf;  // per record: transform chain of its item
+    uint32_t cur_item_xf = 0;
     std::string err;
     explicit stream_builder(const rtnw_scene_desc& desc) : d(desc) {}
 
@@ -316,6 +336,7 @@ struct stream_builder {
         r.b = make_float4(bx, by, ubits(tag), bits(w));
         recs.push_back(r);
         leaf.push_back(leaf_id);
+        rec_xf.push_back(cur_item_xf);
     }
 
     // Append the records of prim slots [first, first+count).  first_cont: narrowing flag of the first primitive;
@@ -377,16 +398,26 @@ struct stream_builder {
         return emit_prims(~ref, count, false, false);
     }
 
-    // bvh_node `idx` whose own box (stored in its parent, or in the item for the root) is [bmin,bmax]
+    // bvh_node `idx` whose own box (stored in its parent, or in the item for the root) is [bmin,bmax].  Preorder:
+    // node, left subtree, right subtree; the tag records which children are leaves and where the right child starts,
+    // b.w is the skip link (first record after the subtree).
     bool emit_node(int32_t idx, const float* bmin, const float* bmax, int depth) {
         if (idx < 0 || idx >= d.n_nodes) return bad("BVH node index out of range");
         if (depth > 4096) return bad("BVH deeper than 4096 levels (cycle?)");
         const rtnw_bvh_node& n = d.nodes[idx];
+        if (n.left == RTNW_REF_NONE) return bad("BVH node without a left child");
         const size_t at = recs.size();
         push(make_float4(bmin[0], bmin[1], bmin[2], bmax[0]), bmax[1], bmax[2], RTNW_TAG(K_NODE, 0, 0, 0), 0, -1);
         if (!emit_child(n.left, n.lcount, n.lmin, n.lmax, depth)) return false;
+        const size_t right_at = recs.size();
         if (!emit_child(n.right, n.rcount, n.rmin, n.rmax, depth)) return false;
-        recs[at].b.w = bits((int32_t)recs.size());  // skip link: first record after the subtree
+        if (right_at - at >= (1u << 24) || recs.size() >= (1u << 24)) return bad("scene exceeds 2^24 records");
+        uint32_t tag = K_NODE | ((uint32_t)(right_at - at) << 8);
+        if (n.left < 0) tag |= RTNW_NODE_LLEAF;
+        if (n.right == RTNW_REF_NONE) tag |= RTNW_NODE_RNONE;
+        else if (n.right < 0) tag |= RTNW_NODE_RLEAF;
+        recs[at].b.z = ubits(tag);
+        recs[at].b.w = bits((int32_t)recs.size());
         return true;
     }
 
@@ -422,6 +453,8 @@ struct stream_builder {
             const rtnw_item& it = d.items[i];
             if (!chain_ok(it.xform)) return false;
             if (it.xform >= (1u << 24)) return bad("transform chain index exceeds 24 bits");
+            cur_item_xf = it.xform;
+            const size_t at = recs.size();
             push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_ITEM, 0, 0, it.xform), (int32_t)it.kind, -1);
             if (it.kind == RTNW_ITEM_PRIMS) {
                 if (!emit_prims(it.first, it.count, true, false)) return false;
@@ -430,8 +463,11 @@ struct stream_builder {
             } else {
                 return bad("unknown item kind");
             }
+            recs[at].a.x = bits((int32_t)recs.size());  // the next element of the top-level list (or K_END)
         }
+        cur_item_xf = 0;
         push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_END, 0, 0, 0), 0, -1);
+        if (recs.size() >= (1u << 24)) return bad("scene exceeds 2^24 records");
         return true;
     }
 };
@@ -448,7 +484,8 @@ template <bool COUNT>
 int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
     int& bps = ctx->blocks_per_sm[COUNT ? 1 : 0];
     if (bps == 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT>, RTNW_BLOCK, 0));
+        CUDA_TRY(cudaFuncSetAttribute(k_render<COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT>, RTNW_BLOCK, sizeof(block_smem)));
         if (bps < 1) bps = 1;
     }
     int blocks = ctx->sm_count * bps;
@@ -456,7 +493,7 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
     const long long blocks_needed = (warps_needed * 32 + RTNW_BLOCK - 1) / RTNW_BLOCK;
     if (blocks_needed < blocks) blocks = (int)blocks_needed;
     if (const char* e = getenv("RTNW_GRID_BLOCKS")) { const int v = atoi(e); if (v > 0) blocks = v; }
-    k_render<COUNT><<<blocks, RTNW_BLOCK, 0, st>>>(a);
+    k_render<COUNT><<<blocks, RTNW_BLOCK, sizeof(block_smem), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RTNW_OK;
 }
@@ -596,6 +633,7 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     size_t off = 0;
     const size_t o_recs = off; off += align256(sz_recs);
     const size_t o_leaf = off; off += align256(sz_leaf);
+    const size_t o_rxf = off; off += align256(sz_leaf);
     const size_t o_xf = off; off += align256(sz_xf);
     const size_t o_mat = off; off += align256(sz_mat);
     const size_t o_tex = off; off += align256(sz_tex);
@@ -605,6 +643,7 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     std::vector<uint8_t> host(off, 0);
     std::memcpy(host.data() + o_recs, sb.recs.data(), sz_recs);
     std::memcpy(host.data() + o_leaf, sb.leaf.data(), sz_leaf);
+    std::memcpy(host.data() + o_rxf, sb.rec_xf.data(), sz_leaf);
     std::memcpy(host.data() + o_xf, desc->xforms, sz_xf);
     if (sz_mat) std::memcpy(host.data() + o_mat, desc->materials, sz_mat);
     if (sz_tex) std::memcpy(host.data() + o_tex, desc->textures, sz_tex);
@@ -624,6 +663,7 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     uint8_t* base = static_cast<uint8_t*>(s->slab);
     s->view.recs = reinterpret_cast<const rec*>(base + o_recs);
     s->view.rec_leaf = reinterpret_cast<const int32_t*>(base + o_leaf);
+    s->view.rec_xf = reinterpret_cast<const uint32_t*>(base + o_rxf);
     s->view.xforms = reinterpret_cast<const rtnw_xform_op*>(base + o_xf);
     s->view.materials = reinterpret_cast<const rtnw_material*>(base + o_mat);
     s->view.textures = reinterpret_cast<const rtnw_texture*>(base + o_tex);
@@ -699,8 +739,10 @@ int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, siz
     CUDA_TRY(d_rays.alloc(n * sizeof(rtnw_ray)));
     CUDA_TRY(d_out.alloc(n * sizeof(rtnw_hit)));
     CUDA_TRY(cudaMemcpyAsync(d_rays.p, rays, n * sizeof(rtnw_ray), cudaMemcpyHostToDevice, ctx->stream));
-    k_trace<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, flags, seed,
-                                                                  d_out.as<rtnw_hit>());
+    (void)flags;  // RTNW_F_CULL_NARROW is accepted for ABI compatibility; the cooperative traversal is always reference-exact
+    CUDA_TRY(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
+    k_trace<<<(unsigned)((n + RTNW_BLOCK - 1) / RTNW_BLOCK), RTNW_BLOCK, sizeof(block_smem), ctx->stream>>>(
+        scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n * sizeof(rtnw_hit), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

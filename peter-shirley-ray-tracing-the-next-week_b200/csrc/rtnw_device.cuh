@@ -53,6 +53,7 @@ struct scene_view {
     const uint8_t* images;
     const float4* ranvec;       // 256 gradients, PSC/perlin.h:82-87
     const uint8_t* perm;        // perm_x | perm_y | perm_z, 256 bytes each, PSC/perlin.h:99-106
+    const uint32_t* rec_xf;     // per record: transform chain of the item it belongs to
     int32_t n_recs, n_materials, n_textures;
 };
 
@@ -91,6 +92,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
+// one copy of the 10 rounds in the binary: draw sites are many (camera, three materials, media) and the render kernel
+// is instruction-cache bound when they are all inlined
+__device__ __noinline__ uint4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    uint4 o;
+    philox4x32_10(c0, c1, c2, c3, k0, k1, o.x, o.y, o.z, o.w);
+    return o;
+}
+
 struct rng_t {                 // sequential stream of one path: draw n = philox(n>>2, 0, sample, pixel)[n&3]
     uint32_t k0, k1, pixel, sample, n;
     uint32_t b0, b1, b2, b3;
@@ -99,16 +108,17 @@ struct rng_t {                 // sequential stream of one path: draw n = philox
     }
     __device__ __forceinline__ float draw() {
         const uint32_t j = n & 3u;
-        if (j == 0) philox4x32_10(n >> 2, 0u, sample, pixel, k0, k1, b0, b1, b2, b3);
+        if (j == 0) {
+            const uint4 o = philox_block(n >> 2, 0u, sample, pixel, k0, k1);
+            b0 = o.x; b1 = o.y; b2 = o.z; b3 = o.w;
+        }
         ++n;
         return u01(j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : b3)));
     }
 };
 // keyed draw of a medium's free-flight number: independent of traversal order and of how often the leaf is tested
 __device__ __forceinline__ float keyed_draw(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t leaf) {
-    uint32_t o0, o1, o2, o3;
-    philox4x32_10(leaf, 1u + depth, sample, pixel, k0, k1, o0, o1, o2, o3);
-    return u01(o0);
+    return u01(philox_block(leaf, 1u + depth, sample, pixel, k0, k1).x);
 }
 
 // PSC/material.h:41-47.  g++ evaluates `vec3(drand48(),drand48(),drand48())` right to left: first draw -> z.
@@ -255,9 +265,13 @@ __device__ __forceinline__ bool hit_medium(const scene_view& S, int i, float4 A,
     const uint32_t chain = tag >> 8;
     if (chain) { xform_ray(S.xforms, chain, r); a = dot(r.d, r.d); }
     const int nb = __float_as_int(A.z);
-    float t1, t2;
-    if (!hit_boundary(S, i + 1, nb, r, a, -FLT_MAX, FLT_MAX, t1)) return false;
-    if (!hit_boundary(S, i + 1, nb, r, a, (float)((double)t1 + 0.0001), FLT_MAX, t2)) return false;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {  // rec1 over (-FLT_MAX, FLT_MAX), then rec2 over (rec1.t + 0.0001, FLT_MAX)
+        float tt;
+        if (!hit_boundary(S, i + 1, nb, r, a, pass ? (float)((double)t1 + 0.0001) : -FLT_MAX, FLT_MAX, tt)) return false;
+        if (pass) t2 = tt; else t1 = tt;
+    }
     if (t1 < t_lo) t1 = t_lo;
     if (t2 > t_hi) t2 = t_hi;
     if (t1 >= t2) return false;
@@ -283,81 +297,299 @@ struct hit_t {
 
 struct trav_counters { uint32_t box_tests, prim_tests; };
 
-// world->hit(r, t_min, t_max, rec), PSC/main.cpp:27.  NARROW (RTNW_F_CULL_NARROW): node boxes are tested against
-// the current best t (with a relative margin) instead of the reference's un-narrowed range.
-template <bool COUNT>
-__device__ __forceinline__ void closest_hit(const scene_view& S, const ray_t& wr, float t_min, float t_max, bool narrow,
-                                            const medium_key& mk, hit_t& h, trav_counters& cnt) {
-    float best_t = t_max;
-    int best = -1, best_face = 0;
-    uint32_t best_xf = 0, item_xf = 0;
-    float tmax0 = t_max, scope_lim = t_max;
-    ray_t r = wr;
-    f3 inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-    float a = dot(r.d, r.d);
-    int i = 0;
-    for (;;) {
-        float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
-        uint32_t tag = __float_as_uint(B.z);
-        // ---- node phase: chase boxes until this lane stands on something else
-        while ((tag & 15u) == K_NODE) {
-            if (COUNT) cnt.box_tests++;
-            // PSC/aabb.h:33-49 with r.origin() (F2): selecting the near/far plane by the sign of invD first is the
-            // reference's swap of (t0,t1) afterwards
-            const float hi = narrow ? best_t + fabsf(best_t) * 1e-4f : tmax0;
-            float lo_t = t_min, hi_t = hi;
-            {
-                const bool neg = inv.x < 0.0f;
-                const float t0 = ((neg ? A.w : A.x) - r.o.x) * inv.x, t1 = ((neg ? A.x : A.w) - r.o.x) * inv.x;
-                lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
-            }
-            {
-                const bool neg = inv.y < 0.0f;
-                const float t0 = ((neg ? B.x : A.y) - r.o.y) * inv.y, t1 = ((neg ? A.y : B.x) - r.o.y) * inv.y;
-                lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
-            }
-            {
-                const bool neg = inv.z < 0.0f;
-                const float t0 = ((neg ? B.y : A.z) - r.o.z) * inv.z, t1 = ((neg ? A.z : B.y) - r.o.z) * inv.z;
-                lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
-            }
-            i = (hi_t <= lo_t) ? __float_as_int(B.w) : i + 1;
-            A = __ldg(&S.recs[i].a); B = __ldg(&S.recs[i].b);
-            tag = __float_as_uint(B.z);
-        }
-        const uint32_t kind = tag & 15u;
-        if (kind == K_END) break;
-        if (kind == K_ITEM) {
-            // next element of the top-level hitable_list: it sees t_max = closest_so_far (PSC/hitable_list.h:25)
-            item_xf = tag >> 8;
-            r = wr;
-            xform_ray(S.xforms, item_xf, r);
-            inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-            a = dot(r.d, r.d);
-            tmax0 = best_t;
-            scope_lim = best_t;
-            ++i;
-            continue;
-        }
-        // ---- primitive phase
-        if (COUNT) cnt.prim_tests++;
-        const float lim = (tag & RTNW_TAG_CONT) ? scope_lim : tmax0;
-        float t; int face = 0; bool hit;
-        int step = 1;
-        if (kind == K_MEDIUM) {
-            hit = hit_medium(S, i, A, tag, r, a, t_min, lim, mk, t);
-            step = 1 + __float_as_int(A.z);
-        } else {
-            hit = hit_surface(S, i, A, B, tag, r, a, t_min, lim, t, face);
-            if (kind == K_MSPHERE) step = 2;
-        }
-        if (hit) {
-            scope_lim = t;
-            if (!(best_t < t)) { best_t = t; best = i; best_face = face; best_xf = item_xf; }
-        }
-        i += step;
+// node record tag bits (above the 4 kind bits): which children are leaves, and where the right child starts
+#define RTNW_NODE_LLEAF 16u
+#define RTNW_NODE_RLEAF 32u
+#define RTNW_NODE_RNONE 64u   // n == 1 node: the reference sets right = left (PSC/bvh.h:106-108)
+
+// The running closest hit of one query as a single 64-bit key, smaller = better:
+//   bits 63..32  t, mapped so that unsigned order == float order
+//   bits 31..3   (2^28-1) - record index: among equal t the LATER record of the stream wins, which is
+//                bvh_node::hit's "right child unless left.t < right.t" (PSC/bvh.h:37-40) and the inclusive
+//                narrowing of rectangles in a list (PSC/aarect.h:52)
+//   bits  2..0   box face
+// so candidates found by different threads combine with one atomicMin.
+typedef unsigned long long hkey_t;
+#define RTNW_KEY_NONE 0xffffffffffffffffull
+__device__ __forceinline__ uint32_t float_order(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float order_float(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ hkey_t make_key(float t, int rec, int face) {
+    return ((hkey_t)float_order(t) << 32) | (hkey_t)(((0x0fffffffu - (uint32_t)rec) << 3) | (uint32_t)face);
+}
+__device__ __forceinline__ float key_t_or(hkey_t k, float t_max) { return k == RTNW_KEY_NONE ? t_max : order_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ int key_rec(hkey_t k) { return (int)(0x0fffffffu - (((uint32_t)k) >> 3)); }
+__device__ __forceinline__ int key_face(hkey_t k) { return (int)(((uint32_t)k) & 7u); }
+
+// bvh_node::hit's `box.hit(r,tmin,tmax)`, PSC/bvh.h:31 + PSC/aabb.h:33-49 with r.origin() (F2).  Selecting the
+// near/far plane by the sign of invD first is the reference's swap of (t0,t1); invD is a function of the ray only.
+__device__ __forceinline__ bool hit_aabb(float4 A, float4 B, f3 o, f3 inv, float t_lo, float t_hi) {
+    float lo_t = t_lo, hi_t = t_hi;
+    {
+        const bool neg = inv.x < 0.0f;
+        const float t0 = ((neg ? A.w : A.x) - o.x) * inv.x, t1 = ((neg ? A.x : A.w) - o.x) * inv.x;
+        lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
     }
-    h.t = best_t; h.rec = best; h.face = best_face; h.xf = best_xf;
+    {
+        const bool neg = inv.y < 0.0f;
+        const float t0 = ((neg ? B.x : A.y) - o.y) * inv.y, t1 = ((neg ? A.y : B.x) - o.y) * inv.y;
+        lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+    }
+    {
+        const bool neg = inv.z < 0.0f;
+        const float t0 = ((neg ? B.y : A.z) - o.z) * inv.z, t1 = ((neg ? A.z : B.y) - o.z) * inv.z;
+        lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+    }
+    return !(hi_t <= lo_t);
+}
+
+// One primitive record (surface or medium) of a scope whose narrowing limit is `lim`; returns records consumed.
+template <bool COUNT>
+__device__ __forceinline__ int test_record(const scene_view& S, int i, float4 A, float4 B, const ray_t& r, float a, float t_min,
+                                           float lim, const medium_key& mk, bool& hit, float& t, int& face, trav_counters& cnt) {
+    const uint32_t tag = __float_as_uint(B.z);
+    const uint32_t kind = tag & 15u;
+    if (COUNT) cnt.prim_tests++;
+    face = 0;
+    if (kind == K_MEDIUM) {
+        hit = hit_medium(S, i, A, tag, r, a, t_min, lim, mk, t);
+        return 1 + __float_as_int(A.z);
+    }
+    hit = hit_surface(S, i, A, B, tag, r, a, t_min, lim, t, face);
+    return kind == K_MSPHERE ? 2 : 1;
+}
+
+// A leaf of a bvh_node (one hitable, possibly a list of several primitives): tested with the UN-narrowed range the
+// node received, narrowing only inside the leaf (PSC/bvh.h:34-35, PSC/hitable_list.h:23-29).  Returns its candidate key.
+template <bool COUNT>
+__device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, const ray_t& r, float a, float t_min, float tmax0,
+                                            const medium_key& mk, trav_counters& cnt) {
+    hkey_t best = RTNW_KEY_NONE;
+    float lim = tmax0;
+    int i = first;
+    for (;;) {
+        const float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
+        bool hit; float t; int face;
+        const int step = test_record<COUNT>(S, i, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
+        if (hit) { lim = t; best = make_key(t, i, face); }  // inside a list the later accepted hit always replaces
+        i += step;
+        const uint32_t tag = __float_as_uint(__ldg(&S.recs[i].b).z);
+        if (!(tag & RTNW_TAG_CONT) || (tag & 15u) >= K_NODE) break;
+    }
+    return best;
+}
+
+// Sequential closest hit over the records [i, end) of a BVH subtree with the skip links (used when a shared-memory
+// queue is full; same result as the cooperative traversal because the leaf set does not depend on the order).
+template <bool COUNT>
+__device__ __noinline__ hkey_t subtree_closest(const scene_view& S, int i, int end, ray_t r, f3 inv, float a, float t_min, float tmax0,
+                                               medium_key mk) {
+    hkey_t best = RTNW_KEY_NONE;
+    trav_counters cnt;
+    cnt.box_tests = 0; cnt.prim_tests = 0;
+    while (i < end) {
+        const float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
+        const uint32_t tag = __float_as_uint(B.z);
+        if ((tag & 15u) == K_NODE) {
+            i = hit_aabb(A, B, r.o, inv, t_min, tmax0) ? i + 1 : __float_as_int(B.w);
+        } else {
+            const hkey_t k = test_leaf<COUNT>(S, i, r, a, t_min, tmax0, mk, cnt);
+            if (k < best) best = k;
+            // advance past the leaf's records
+            for (;;) {
+                const uint32_t tg = __float_as_uint(__ldg(&S.recs[i].b).z);
+                const uint32_t kd = tg & 15u;
+                i += kd == K_MEDIUM ? 1 + __float_as_int(__ldg(&S.recs[i].a).z) : (kd == K_MSPHERE ? 2 : 1);
+                const uint32_t nt = __float_as_uint(__ldg(&S.recs[i].b).z);
+                if (!(nt & RTNW_TAG_CONT) || (nt & 15u) >= K_NODE) break;
+            }
+        }
+    }
+    return best;
+}
+
+// ---- block-cooperative closest hit --------------------------------------------------------------------------
+// Every thread of the block owns one ray (or none).  All rays walk the same record stream, item by item:
+//   * a list item (PSC/hitable_list.h:20-32) is scanned by each owner in lockstep: same records, same code, all lanes;
+//   * a BVH item is traversed by the WHOLE BLOCK through shared-memory queues.  Because bvh_node::hit gives both
+//     children the un-narrowed range (PSC/bvh.h:34-35) the set of nodes/leaves a ray tests is order independent, so
+//     the (ray, node) box tests of all rays of the block are done level by level as uniform tasks (any thread takes
+//     any task), the reached (ray, leaf) pairs are collected, and then tested as uniform tasks as well; candidates
+//     are merged per ray with atomicMin on the 64-bit key.  Neither phase has per-lane control flow to diverge on.
+#ifndef RTNW_QN
+#define RTNW_QN 3072  // capacity of each node frontier and of the leaf queue, in tasks
+#endif
+template <int BLOCK>
+struct coop_smem {
+    float4 ray_o[BLOCK];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
+    float4 ray_d[BLOCK];  // d.xyz, w = dot(d,d)
+    float4 ray_i[BLOCK];  // 1/d, w = time
+    uint4 mkey[BLOCK];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
+    hkey_t key[BLOCK];
+    uint32_t q[2][RTNW_QN];
+    uint32_t ql[RTNW_QN];
+    int n[3];
+    int nl;
+};
+#define RTNW_TASK(slot, rec) (((uint32_t)(slot) << 24) | (uint32_t)(rec))
+
+// warp-aggregated append of up to two entries per lane: returns false for an entry that did not fit
+__device__ __forceinline__ void queue_push2(uint32_t* q, int* count, int cap, bool p0, uint32_t v0, bool p1, uint32_t v1,
+                                            bool& spill0, bool& spill1) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned b0 = __ballot_sync(FULL, p0), b1 = __ballot_sync(FULL, p1);
+    spill0 = false; spill1 = false;
+    const int total = __popc(b0) + __popc(b1);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, total);
+    base = __shfl_sync(FULL, base, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (p0) {
+        const int at = base + __popc(b0 & lt);
+        if (at < cap) q[at] = v0; else spill0 = true;
+    }
+    if (p1) {
+        const int at = base + __popc(b0) + __popc(b1 & lt);
+        if (at < cap) q[at] = v1; else spill1 = true;
+    }
+}
+
+// Closest hit of the block's rays against the BVH item whose root node record is `root`.  Owners have already
+// written their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Must be called by all threads.
+template <int BLOCK, bool COUNT>
+__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, bool active, float t_min,
+                                              uint32_t k0, uint32_t k1, trav_counters& cnt) {
+    const int tid = threadIdx.x;
+    if (tid < 3) sm.n[tid] = 0;
+    if (tid == 3) sm.nl = 0;
+    __syncthreads();
+    {   // level 0: one task per active ray
+        bool s0, s1;
+        queue_push2(sm.q[0], &sm.n[0], RTNW_QN, active, RTNW_TASK(tid, root), false, 0u, s0, s1);
+    }
+    __syncthreads();
+    // ---- node phase: level-synchronous, every task is one aabb::hit
+    for (int level = 0;; ++level) {
+        const int n = min(sm.n[level % 3], RTNW_QN);
+        if (n == 0) break;
+        const uint32_t* cur = sm.q[level & 1];
+        uint32_t* nxt = sm.q[(level + 1) & 1];
+        int* n_nxt = &sm.n[(level + 1) % 3];
+        if (tid == 0) sm.n[(level + 2) % 3] = 0;  // consumed two levels ago, filled again at the next level
+        for (int base = 0; base < n; base += BLOCK) {
+            const int q = base + tid;
+            bool pn0 = false, pn1 = false, pl0 = false, pl1 = false;
+            uint32_t c0 = 0, c1 = 0;
+            int slot = 0;
+            if (q < n) {
+                const uint32_t task = cur[q];
+                slot = (int)(task >> 24);
+                const int rec = (int)(task & 0xffffffu);
+                const float4 A = __ldg(&S.recs[rec].a), B = __ldg(&S.recs[rec].b);
+                const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
+                if (COUNT) cnt.box_tests++;
+                if (hit_aabb(A, B, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w)) {
+                    const uint32_t tag = __float_as_uint(B.z);
+                    c0 = RTNW_TASK(slot, rec + 1);
+                    c1 = RTNW_TASK(slot, rec + (int)(tag >> 8));
+                    const bool has_r = !(tag & RTNW_NODE_RNONE);
+                    pl0 = (tag & RTNW_NODE_LLEAF) != 0; pn0 = !pl0;
+                    pl1 = has_r && (tag & RTNW_NODE_RLEAF) != 0; pn1 = has_r && !pl1;
+                }
+            }
+            bool sn0, sn1, sl0, sl1;
+            queue_push2(nxt, n_nxt, RTNW_QN, pn0, c0, pn1, c1, sn0, sn1);
+            queue_push2(sm.ql, &sm.nl, RTNW_QN, pl0, c0, pl1, c1, sl0, sl1);
+            if (sn0 | sn1 | sl0 | sl1) {  // a queue is full: finish those children right here, sequentially
+                const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
+                const uint4 mq = sm.mkey[slot];
+                ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+                medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
+                hkey_t best = RTNW_KEY_NONE;
+                for (int w = 0; w < 2; ++w) {
+                    const bool sp = w ? (sn1 | sl1) : (sn0 | sl0);
+                    if (!sp) continue;
+                    const int c = (int)((w ? c1 : c0) & 0xffffffu);
+                    const bool is_node = w ? sn1 : sn0;
+                    const int end = is_node ? __float_as_int(__ldg(&S.recs[c].b).w) : c + 1;
+                    const hkey_t k = subtree_closest<COUNT>(S, c, is_node ? end : c + 1, r, mk3(ri.x, ri.y, ri.z), rd.w, t_min, ro.w, mk);
+                    if (k < best) best = k;
+                }
+                if (best != RTNW_KEY_NONE) atomicMin(&sm.key[slot], best);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- leaf phase: every task is one leaf->hit(r, tmin, tmax0)
+    const int nl = min(sm.nl, RTNW_QN);
+    for (int q = tid; q < nl; q += BLOCK) {
+        const uint32_t task = sm.ql[q];
+        const int slot = (int)(task >> 24), rec = (int)(task & 0xffffffu);
+        const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
+        const uint4 mq = sm.mkey[slot];
+        ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+        medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
+        const hkey_t k = test_leaf<COUNT>(S, rec, r, rd.w, t_min, ro.w, mk, cnt);
+        if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
+    }
+    __syncthreads();
+}
+
+// world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
+// thread without a ray passes active = false and still works on the other threads' BVH tasks.
+template <int BLOCK, bool COUNT>
+__device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_smem<BLOCK>& sm, const ray_t& wr, bool active,
+                                                   float t_min, float t_max, const medium_key& mk, trav_counters& cnt) {
+    const int tid = threadIdx.x;
+    sm.key[tid] = RTNW_KEY_NONE;
+    sm.mkey[tid] = make_uint4(mk.pixel, mk.sample, mk.depth, 0u);
+    int i = 0;
+    for (;;) {  // the elements of the top-level hitable_list, in order (PSC/hitable_list.h:24-30); uniform over the block
+        const float4 IA = __ldg(&S.recs[i].a), IB = __ldg(&S.recs[i].b);
+        const uint32_t tag = __float_as_uint(IB.z);
+        if ((tag & 15u) != K_ITEM) break;  // K_END
+        const int next = __float_as_int(IA.x);
+        hkey_t key = sm.key[tid];
+        const float best_t = key_t_or(key, t_max);  // closest_so_far: the t_max this element receives
+        ray_t r = wr;
+        xform_ray(S.xforms, tag >> 8, r);
+        const float a = dot(r.d, r.d);
+        if (__float_as_int(IB.w) == RTNW_ITEM_BVH) {
+            sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
+            sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
+            sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
+            coop_bvh_item<BLOCK, COUNT>(S, sm, i + 1, active, t_min, mk.k0, mk.k1, cnt);
+        } else if (active) {
+            float lim = best_t;
+            for (int j = i + 1; j < next;) {
+                const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
+                bool hit; float t; int face;
+                const int step = test_record<COUNT>(S, j, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
+                if (hit) { lim = t; key = make_key(t, j, face); }  // list narrowing: an accepted hit is the new closest
+                j += step;
+            }
+            sm.key[tid] = key;
+        }
+        i = next;
+    }
+    __syncthreads();  // nobody may overwrite sm.key before every owner has read its result
+    const hkey_t out = sm.key[tid];
+    __syncthreads();
+    return out;
+}
+
+__device__ __forceinline__ void key_to_hit(const scene_view& S, hkey_t key, float t_max, hit_t& h) {
+    if (key == RTNW_KEY_NONE) { h.rec = -1; h.t = t_max; h.face = 0; h.xf = 0; return; }
+    h.rec = key_rec(key);
+    h.face = key_face(key);
+    h.t = order_float((uint32_t)(key >> 32));
+    h.xf = __ldg(&S.rec_xf[h.rec]);
 }
 
 // PSC/hitable.h:14-19
@@ -520,56 +752,58 @@ __device__ __forceinline__ f3 material_emitted(const scene_view& S, int mat, flo
     if (__float_as_uint(m0.x) != RTNW_MAT_DIFFUSE_LIGHT) return mk3(0.f, 0.f, 0.f);
     return texture_value(S, __float_as_int(m0.y), u, v, p);
 }
-// material::scatter(r_in, rec, attenuation, scattered), PSC/material.h:64-149
+// material::scatter(r_in, rec, attenuation, scattered), PSC/material.h:64-149.  lambertian, metal and isotropic each
+// draw exactly one random_in_unit_sphere() and nothing else, and two of them end with one texture lookup, so both are
+// evaluated at a single site (draw order inside each material is unchanged: reflect() and value() draw nothing).
 __device__ __forceinline__ bool material_scatter(const scene_view& S, int mat, const ray_t& r_in, const surf_t& s, rng_t& g,
                                                  f3& attenuation, ray_t& scattered) {
     const float4 m0 = __ldg(reinterpret_cast<const float4*>(S.materials + mat));      // kind, tex, f, pad
     const uint32_t kind = __float_as_uint(m0.x);
-    switch (kind) {
-        case RTNW_MAT_LAMBERTIAN: {
-            const f3 target = s.p + s.n + random_in_unit_sphere(g);
-            scattered.o = s.p; scattered.d = target - s.p; scattered.time = r_in.time;
-            attenuation = texture_value(S, __float_as_int(m0.y), s.u, s.v, s.p);
-            return true;
+    if (kind == RTNW_MAT_DIFFUSE_LIGHT) return false;
+    scattered.o = s.p;
+    if (kind == RTNW_MAT_DIELECTRIC) {
+        const float ref_idx = m0.z;
+        f3 outward_normal;
+        const f3 reflected = reflect(r_in.d, s.n);
+        float ni_over_nt, reflect_prob, cosine;
+        attenuation = mk3(1.f, 1.f, 1.f);
+        f3 refracted = mk3(0.f, 0.f, 0.f);
+        const float dn = dot(r_in.d, s.n);
+        if (dn > 0.f) {
+            outward_normal = -s.n;
+            ni_over_nt = ref_idx;
+            cosine = dn / length(r_in.d);
+            cosine = sqrtf(1.f - ref_idx * ref_idx * (1.f - cosine * cosine));
+        } else {
+            outward_normal = s.n;
+            ni_over_nt = 1.0f / ref_idx;
+            cosine = -dn / length(r_in.d);
         }
-        case RTNW_MAT_METAL: {
-            const float4 m1 = __ldg(reinterpret_cast<const float4*>(S.materials + mat) + 1);  // albedo
-            const f3 reflected = reflect(unit_vector(r_in.d), s.n);
-            scattered.o = s.p; scattered.d = reflected + m0.z * random_in_unit_sphere(g); scattered.time = 0.f;
-            attenuation = mk3(m1.x, m1.y, m1.z);
-            return dot(scattered.d, s.n) > 0.f;
-        }
-        case RTNW_MAT_DIELECTRIC: {
-            const float ref_idx = m0.z;
-            f3 outward_normal;
-            const f3 reflected = reflect(r_in.d, s.n);
-            float ni_over_nt, reflect_prob, cosine;
-            attenuation = mk3(1.f, 1.f, 1.f);
-            f3 refracted = mk3(0.f, 0.f, 0.f);
-            const float dn = dot(r_in.d, s.n);
-            if (dn > 0.f) {
-                outward_normal = -s.n;
-                ni_over_nt = ref_idx;
-                cosine = dn / length(r_in.d);
-                cosine = sqrtf(1.f - ref_idx * ref_idx * (1.f - cosine * cosine));
-            } else {
-                outward_normal = s.n;
-                ni_over_nt = 1.0f / ref_idx;
-                cosine = -dn / length(r_in.d);
-            }
-            if (refract(r_in.d, outward_normal, ni_over_nt, refracted)) reflect_prob = schlick(cosine, ref_idx);
-            else reflect_prob = 1.0f;
-            scattered.o = s.p; scattered.time = 0.f;
-            scattered.d = (g.draw() < reflect_prob) ? reflected : refracted;
-            return true;
-        }
-        case RTNW_MAT_ISOTROPIC: {
-            scattered.o = s.p; scattered.d = random_in_unit_sphere(g); scattered.time = 0.f;
-            attenuation = texture_value(S, __float_as_int(m0.y), s.u, s.v, s.p);
-            return true;
-        }
-        default: return false;  // diffuse_light
+        if (refract(r_in.d, outward_normal, ni_over_nt, refracted)) reflect_prob = schlick(cosine, ref_idx);
+        else reflect_prob = 1.0f;
+        scattered.time = 0.f;
+        scattered.d = (g.draw() < reflect_prob) ? reflected : refracted;
+        return true;
     }
+    const f3 rs = random_in_unit_sphere(g);
+    if (kind == RTNW_MAT_METAL) {
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(S.materials + mat) + 1);  // albedo
+        const f3 reflected = reflect(unit_vector(r_in.d), s.n);
+        scattered.d = reflected + m0.z * rs;
+        scattered.time = 0.f;
+        attenuation = mk3(m1.x, m1.y, m1.z);
+        return dot(scattered.d, s.n) > 0.f;
+    }
+    if (kind == RTNW_MAT_LAMBERTIAN) {
+        const f3 target = s.p + s.n + rs;
+        scattered.d = target - s.p;
+        scattered.time = r_in.time;
+    } else {  // isotropic
+        scattered.d = rs;
+        scattered.time = 0.f;
+    }
+    attenuation = texture_value(S, __float_as_int(m0.y), s.u, s.v, s.p);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------ camera

@@ -73,7 +73,7 @@ def test_closest_hit_ids_bit_exact(rtnw, ctx, name):
     hs = rtnw.HostScene(name)
     ds = ctx.upload(hs.desc_ptr)
     got = ds.trace(rays, 0.001, FLT_MAX, flags=0, seed=11)
-    assert (want["prim_id"] >= 0).sum() > len(rays) // 4
+    assert (want["prim_id"] >= 0).sum() > len(rays) // 10
     assert_hits_equal(got, want)
     # mat_id is this framework's table index: check it names the same material kind the reference hit
     ds.close()
