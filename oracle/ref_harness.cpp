@@ -14,7 +14,8 @@
 //   * counters: `ref_cnt[k]++` at the top of aabb::hit / sphere::hit / moving_sphere::hit / x?_rect::hit /
 //     constant_medium::hit, for the per-ray test counts the roofline uses;
 //   * `#define drand48 ref_hook_drand48`: scene construction still gets glibc's drand48; while rendering with
-//     rng_mode=1 the draws come from the framework's counter-based stream (Philox4x32-10) so the
+//     rng_mode=1 the draws come from the framework's stream (Philox4x32-10 keyed by (seed; pixel, sample) seeding
+//     the drand48 recurrence, media drawing keyed Philox numbers) so the
 //     reference and the GPU consume the SAME random numbers and their images can be compared sample for sample.
 //
 // Leaf ids: hit_record has no primitive id, so every leaf handed to the list/BVH is wrapped in a
@@ -46,14 +47,13 @@ namespace {
 struct philox_state {
     uint32_t key[2];
     uint32_t pixel, sample;
-    uint32_t seq;        // next sequential draw
+    uint64_t x;          // state of the path's sequential stream (drand48 recurrence, seeded by Philox)
+    int seeded;          // x holds the state of the current (pixel, sample)
     int depth;           // index of the current top-level closest-hit query in this path
     int leaf;            // >= 0 while inside a tagged leaf's hit() (medium free-flight draws are keyed by it)
     int mode;            // 0 = glibc drand48 (scene construction, native baseline), 1 = Philox streams
-    uint32_t block[4];   // cached block of the sequential stream
-    uint32_t block_idx;
     uint64_t draws;
-} G = {{0, 0}, 0, 0, 0, 0, -1, 0, {0, 0, 0, 0}, 0xffffffffu, 0};
+} G = {{0, 0}, 0, 0, 0, 0, 0, -1, 0, 0};
 
 inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
@@ -81,22 +81,24 @@ double hook_stream_draw() {
         philox4x32_10(ctr, G.key, out);
         return u01(out[0]);
     }
-    const uint32_t n = G.seq++;
-    if ((n >> 2) != G.block_idx) {
-        const uint32_t ctr[4] = {n >> 2, 0u, G.sample, G.pixel};
-        philox4x32_10(ctr, G.key, G.block);
-        G.block_idx = n >> 2;
+    // sequential stream of the path: Philox(0, 0, sample, pixel) seeds the drand48 recurrence
+    if (!G.seeded) {
+        const uint32_t ctr[4] = {0u, 0u, G.sample, G.pixel};
+        uint32_t out[4];
+        philox4x32_10(ctr, G.key, out);
+        G.x = ((uint64_t)(out[1] & 0xffffu) << 32) | (uint64_t)out[0];
+        G.seeded = 1;
     }
-    return u01(G.block[n & 3]);
+    G.x = (G.x * 0x5DEECE66DULL + 0xBULL) & 0xffffffffffffULL;
+    return (double)((float)(uint32_t)(G.x >> 24) * (1.0f / 16777216.0f));
 }
 
 inline void begin_path(uint32_t pixel, uint32_t sample) {
     G.pixel = pixel;
     G.sample = sample;
-    G.seq = 0;
+    G.seeded = 0;
     G.depth = -1;
     G.leaf = -1;
-    G.block_idx = 0xffffffffu;
 }
 
 }  // namespace

@@ -155,7 +155,7 @@ def device_lib() -> C.CDLL:
     """Load librtnw.so.  Fails loudly when it is missing: the product path has no CPU fallback."""
     global _dev
     if _dev is None:
-        path = LIB_DIR / "librtnw.so"
+        path = Path(os.environ.get("RTNW_LIB", LIB_DIR / "librtnw.so"))  # RTNW_LIB: A/B builds while tuning
         if not path.exists():
             raise RtnwError(RTNW_ERR_CUDA, f"{path} is missing: the CUDA extension must be built "
                                            f"(__graft_entry__.build()); there is no CPU fallback")

@@ -4,6 +4,7 @@
 // implementation in this library: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +18,9 @@ using namespace rtnw_dev;
 
 #ifndef RTNW_BLOCK
 #define RTNW_BLOCK 128
+#endif
+#ifndef RTNW_MIN_BLOCKS
+#define RTNW_MIN_BLOCKS 3   // resident blocks per SM the register allocation is sized for
 #endif
 
 // ================================================================================================ kernels
@@ -42,7 +46,7 @@ typedef coop_smem<RTNW_BLOCK> block_smem;
 // A per-lane traversal state machine was measured at 2-13 active lanes of 32 per instruction (profiles/r1-r3*.txt);
 // this form keeps every phase uniform across the warp.
 template <bool COUNT>
-__global__ void __launch_bounds__(RTNW_BLOCK) k_render(const render_args P) {
+__global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const render_args P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     block_smem& sm = *reinterpret_cast<block_smem*>(smem_raw);
     constexpr unsigned FULL = 0xffffffffu;
@@ -392,38 +396,45 @@ struct stream_builder {
         return true;
     }
 
-    bool emit_child(int32_t ref, int32_t count, const float* bmin, const float* bmax, int depth) {
-        if (ref == RTNW_REF_NONE) return true;
-        if (ref >= 0) return emit_node(ref, bmin, bmax, depth + 1);
-        return emit_prims(~ref, count, false, false);
-    }
+    std::vector<float4> nodes2;        // 4 float4 per bvh_node, children rewritten (see scene_view::nodes)
+    std::vector<uint8_t> node_seen;
 
-    // bvh_node `idx` whose own box (stored in its parent, or in the item for the root) is [bmin,bmax].  Preorder:
-    // node, left subtree, right subtree; the tag records which children are leaves and where the right child starts,
-    // b.w is the skip link (first record after the subtree).
-    bool emit_node(int32_t idx, const float* bmin, const float* bmax, int depth) {
+    // bvh_node `idx`: leaves are appended to the record stream in left-to-right order (the key's tie rule relies on
+    // it), the node itself goes to the two-box table with its leaf children rewritten to record indices.
+    bool emit_node(int32_t idx, int depth) {
         if (idx < 0 || idx >= d.n_nodes) return bad("BVH node index out of range");
-        if (depth > 4096) return bad("BVH deeper than 4096 levels (cycle?)");
+        if (depth >= 60) return bad("BVH deeper than 60 levels");
+        if (node_seen[idx]) return bad("BVH node referenced twice");
+        node_seen[idx] = 1;
         const rtnw_bvh_node& n = d.nodes[idx];
         if (n.left == RTNW_REF_NONE) return bad("BVH node without a left child");
-        const size_t at = recs.size();
-        push(make_float4(bmin[0], bmin[1], bmin[2], bmax[0]), bmax[1], bmax[2], RTNW_TAG(K_NODE, 0, 0, 0), 0, -1);
-        if (!emit_child(n.left, n.lcount, n.lmin, n.lmax, depth)) return false;
-        const size_t right_at = recs.size();
-        if (!emit_child(n.right, n.rcount, n.rmin, n.rmax, depth)) return false;
-        if (right_at - at >= (1u << 24) || recs.size() >= (1u << 24)) return bad("scene exceeds 2^24 records");
-        uint32_t tag = K_NODE | ((uint32_t)(right_at - at) << 8);
-        if (n.left < 0) tag |= RTNW_NODE_LLEAF;
-        if (n.right == RTNW_REF_NONE) tag |= RTNW_NODE_RNONE;
-        else if (n.right < 0) tag |= RTNW_NODE_RLEAF;
-        recs[at].b.z = ubits(tag);
-        recs[at].b.w = bits((int32_t)recs.size());
+        int32_t child[2] = {n.left, n.right};
+        const int32_t cnt[2] = {n.lcount, n.rcount};
+        for (int w = 0; w < 2; ++w) {
+            if (child[w] == RTNW_REF_NONE) continue;
+            if (child[w] >= 0) {
+                if (!emit_node(child[w], depth + 1)) return false;
+            } else {
+                const size_t first = recs.size();
+                if (!emit_prims(~child[w], cnt[w], false, false)) return false;
+                if (recs.size() == first) return bad("empty BVH leaf");
+                child[w] = ~(int32_t)first;
+            }
+        }
+        if (recs.size() >= (1u << 24)) return bad("scene exceeds 2^24 records");
+        nodes2[4 * (size_t)idx + 0] = make_float4(n.lmin[0], n.lmin[1], n.lmin[2], bits(child[0]));
+        nodes2[4 * (size_t)idx + 1] = make_float4(n.lmax[0], n.lmax[1], n.lmax[2], bits(child[1]));
+        nodes2[4 * (size_t)idx + 2] = make_float4(n.rmin[0], n.rmin[1], n.rmin[2], 0.f);
+        nodes2[4 * (size_t)idx + 3] = make_float4(n.rmax[0], n.rmax[1], n.rmax[2], 0.f);
         return true;
     }
 
     bool run() {
         if (d.abi_version != RTNW_ABI_VERSION) return bad("scene_desc.abi_version does not match this library");
         if (d.n_items <= 0 || !d.items) return bad("scene has no items");
+        if (d.n_nodes >= (1 << 24)) return bad("scene exceeds 2^24 BVH nodes");
+        nodes2.assign(4 * (size_t)std::max(d.n_nodes, 1), make_float4(0, 0, 0, 0));
+        node_seen.assign((size_t)std::max(d.n_nodes, 1), 0);
         if (d.n_prim_slots < 0 || d.n_nodes < 0 || d.n_materials < 0 || d.n_textures < 0 || d.n_xform_ops < 1)
             return bad("negative table size (or missing identity transform op 0)");
         if ((d.n_prim_slots && !d.prims) || (d.n_nodes && !d.nodes) || (d.n_materials && !d.materials) ||
@@ -459,7 +470,10 @@ struct stream_builder {
             if (it.kind == RTNW_ITEM_PRIMS) {
                 if (!emit_prims(it.first, it.count, true, false)) return false;
             } else if (it.kind == RTNW_ITEM_BVH) {
-                if (!emit_node(it.first, it.bmin, it.bmax, 0)) return false;
+                // second record of the item: the root bvh_node's own box; then the leaves of the tree
+                recs[at].a.y = bits(it.first);
+                push(make_float4(it.bmin[0], it.bmin[1], it.bmin[2], it.bmax[0]), it.bmax[1], it.bmax[2], RTNW_TAG(K_EXT, 0, 1, 0), 0, -1);
+                if (!emit_node(it.first, 0)) return false;
             } else {
                 return bad("unknown item kind");
             }
@@ -634,6 +648,8 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     const size_t o_recs = off; off += align256(sz_recs);
     const size_t o_leaf = off; off += align256(sz_leaf);
     const size_t o_rxf = off; off += align256(sz_leaf);
+    const size_t sz_nodes = sb.nodes2.size() * sizeof(float4);
+    const size_t o_nodes = off; off += align256(sz_nodes);
     const size_t o_xf = off; off += align256(sz_xf);
     const size_t o_mat = off; off += align256(sz_mat);
     const size_t o_tex = off; off += align256(sz_tex);
@@ -644,6 +660,7 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     std::memcpy(host.data() + o_recs, sb.recs.data(), sz_recs);
     std::memcpy(host.data() + o_leaf, sb.leaf.data(), sz_leaf);
     std::memcpy(host.data() + o_rxf, sb.rec_xf.data(), sz_leaf);
+    std::memcpy(host.data() + o_nodes, sb.nodes2.data(), sz_nodes);
     std::memcpy(host.data() + o_xf, desc->xforms, sz_xf);
     if (sz_mat) std::memcpy(host.data() + o_mat, desc->materials, sz_mat);
     if (sz_tex) std::memcpy(host.data() + o_tex, desc->textures, sz_tex);
@@ -664,6 +681,7 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     s->view.recs = reinterpret_cast<const rec*>(base + o_recs);
     s->view.rec_leaf = reinterpret_cast<const int32_t*>(base + o_leaf);
     s->view.rec_xf = reinterpret_cast<const uint32_t*>(base + o_rxf);
+    s->view.nodes = reinterpret_cast<const float4*>(base + o_nodes);
     s->view.xforms = reinterpret_cast<const rtnw_xform_op*>(base + o_xf);
     s->view.materials = reinterpret_cast<const rtnw_material*>(base + o_mat);
     s->view.textures = reinterpret_cast<const rtnw_texture*>(base + o_tex);

@@ -54,6 +54,8 @@ struct scene_view {
     const float4* ranvec;       // 256 gradients, PSC/perlin.h:82-87
     const uint8_t* perm;        // perm_x | perm_y | perm_z, 256 bytes each, PSC/perlin.h:99-106
     const uint32_t* rec_xf;     // per record: transform chain of the item it belongs to
+    const float4* nodes;        // 4 float4 per bvh_node: {lmin, left} {lmax, right} {rmin, -} {rmax, -}; child >= 0: node
+                                // index, child < 0: ~(first record of the leaf), RTNW_REF_NONE: absent
     int32_t n_recs, n_materials, n_textures;
 };
 
@@ -92,28 +94,29 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-// one copy of the 10 rounds in the binary: draw sites are many (camera, three materials, media) and the render kernel
-// is instruction-cache bound when they are all inlined
+// one copy of the 10 rounds in the binary (path seeding and medium draws call it)
 __device__ __noinline__ uint4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     uint4 o;
     philox4x32_10(c0, c1, c2, c3, k0, k1, o.x, o.y, o.z, o.w);
     return o;
 }
 
-struct rng_t {                 // sequential stream of one path: draw n = philox(n>>2, 0, sample, pixel)[n&3]
-    uint32_t k0, k1, pixel, sample, n;
-    uint32_t b0, b1, b2, b3;
+// The sequential stream of one path: Philox(counter = (0, 0, sample, pixel), key = seed) gives the 48-bit
+// initial state, and the stream itself is the reference's own generator, the drand48 recurrence
+// X <- (0x5DEECE66D * X + 0xB) mod 2^48 (glibc), of which a draw returns the top 24 bits as a float in [0,1).
+// Counter-based where it matters (any path can be started anywhere, on any GPU), and a draw costs one 64-bit
+// multiply-add instead of a quarter of a Philox block, with no data-dependent refill to diverge on.
+struct rng_t {
+    unsigned long long x;
+    uint32_t sample;
     __device__ __forceinline__ void begin(uint32_t key0, uint32_t key1, uint32_t px, uint32_t s) {
-        k0 = key0; k1 = key1; pixel = px; sample = s; n = 0;
+        const uint4 o = philox_block(0u, 0u, s, px, key0, key1);
+        x = ((unsigned long long)(o.y & 0xffffu) << 32) | (unsigned long long)o.x;
+        sample = s;
     }
     __device__ __forceinline__ float draw() {
-        const uint32_t j = n & 3u;
-        if (j == 0) {
-            const uint4 o = philox_block(n >> 2, 0u, sample, pixel, k0, k1);
-            b0 = o.x; b1 = o.y; b2 = o.z; b3 = o.w;
-        }
-        ++n;
-        return u01(j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : b3)));
+        x = (x * 0x5DEECE66Dull + 0xBull) & 0xffffffffffffull;
+        return (float)(uint32_t)(x >> 24) * (1.0f / 16777216.0f);
     }
 };
 // keyed draw of a medium's free-flight number: independent of traversal order and of how often the leaf is tested
@@ -244,6 +247,7 @@ __device__ __forceinline__ bool hit_surface(const scene_view& S, int i, float4 A
 __device__ __forceinline__ bool hit_boundary(const scene_view& S, int first, int nb, const ray_t& r, float a, float t_lo, float t_hi, float& t) {
     bool any = false;
     float lim = t_hi;
+#pragma unroll 1
     for (int i = first; i < first + nb; ++i) {
         const float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
         const uint32_t tag = __float_as_uint(B.z);
@@ -258,7 +262,7 @@ __device__ __forceinline__ bool hit_boundary(const scene_view& S, int first, int
 struct medium_key { uint32_t k0, k1, pixel, sample, depth; };
 
 // PSC/constant_medium.h:26-50
-__device__ __forceinline__ bool hit_medium(const scene_view& S, int i, float4 A, uint32_t tag, const ray_t& r_frame, float a_frame,
+__device__ __noinline__ bool hit_medium(const scene_view& S, int i, float4 A, uint32_t tag, const ray_t& r_frame, float a_frame,
                                            float t_lo, float t_hi, const medium_key& mk, float& t) {
     ray_t r = r_frame;
     float a = a_frame;
@@ -296,11 +300,6 @@ struct hit_t {
 };
 
 struct trav_counters { uint32_t box_tests, prim_tests; };
-
-// node record tag bits (above the 4 kind bits): which children are leaves, and where the right child starts
-#define RTNW_NODE_LLEAF 16u
-#define RTNW_NODE_RLEAF 32u
-#define RTNW_NODE_RNONE 64u   // n == 1 node: the reference sets right = left (PSC/bvh.h:106-108)
 
 // The running closest hit of one query as a single 64-bit key, smaller = better:
 //   bits 63..32  t, mapped so that unsigned order == float order
@@ -383,29 +382,32 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
     return best;
 }
 
-// Sequential closest hit over the records [i, end) of a BVH subtree with the skip links (used when a shared-memory
-// queue is full; same result as the cooperative traversal because the leaf set does not depend on the order).
+// Sequential closest hit below one bvh_node whose own box already passed (used when a shared-memory queue is full;
+// same result as the cooperative traversal because the set of leaves a ray tests does not depend on the order).
 template <bool COUNT>
-__device__ __noinline__ hkey_t subtree_closest(const scene_view& S, int i, int end, ray_t r, f3 inv, float a, float t_min, float tmax0,
+__device__ __noinline__ hkey_t subtree_closest(const scene_view& S, int node, ray_t r, f3 inv, float a, float t_min, float tmax0,
                                                medium_key mk) {
     hkey_t best = RTNW_KEY_NONE;
     trav_counters cnt;
     cnt.box_tests = 0; cnt.prim_tests = 0;
-    while (i < end) {
-        const float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
-        const uint32_t tag = __float_as_uint(B.z);
-        if ((tag & 15u) == K_NODE) {
-            i = hit_aabb(A, B, r.o, inv, t_min, tmax0) ? i + 1 : __float_as_int(B.w);
-        } else {
-            const hkey_t k = test_leaf<COUNT>(S, i, r, a, t_min, tmax0, mk, cnt);
-            if (k < best) best = k;
-            // advance past the leaf's records
-            for (;;) {
-                const uint32_t tg = __float_as_uint(__ldg(&S.recs[i].b).z);
-                const uint32_t kd = tg & 15u;
-                i += kd == K_MEDIUM ? 1 + __float_as_int(__ldg(&S.recs[i].a).z) : (kd == K_MSPHERE ? 2 : 1);
-                const uint32_t nt = __float_as_uint(__ldg(&S.recs[i].b).z);
-                if (!(nt & RTNW_TAG_CONT) || (nt & 15u) >= K_NODE) break;
+    int stack[64];  // depth is validated at upload
+    int sp = 0;
+    stack[sp++] = node;
+    while (sp > 0) {
+        const int n = stack[--sp];
+        const float4 n0 = __ldg(&S.nodes[4 * n]), n1 = __ldg(&S.nodes[4 * n + 1]);
+        const float4 n2 = __ldg(&S.nodes[4 * n + 2]), n3 = __ldg(&S.nodes[4 * n + 3]);
+        const int left = __float_as_int(n0.w), right = __float_as_int(n1.w);
+        for (int w = 0; w < 2; ++w) {
+            const int c = w ? right : left;
+            if (c == RTNW_REF_NONE) continue;
+            if (c >= 0) {
+                const float4 lo = w ? n2 : n0, hi = w ? n3 : n1;
+                if (hit_aabb(make_float4(lo.x, lo.y, lo.z, hi.x), make_float4(hi.y, hi.z, 0.f, 0.f), r.o, inv, t_min, tmax0) && sp < 64)
+                    stack[sp++] = c;
+            } else {
+                const hkey_t k = test_leaf<COUNT>(S, ~c, r, a, t_min, tmax0, mk, cnt);
+                if (k < best) best = k;
             }
         }
     }
@@ -417,11 +419,15 @@ __device__ __noinline__ hkey_t subtree_closest(const scene_view& S, int i, int e
 //   * a list item (PSC/hitable_list.h:20-32) is scanned by each owner in lockstep: same records, same code, all lanes;
 //   * a BVH item is traversed by the WHOLE BLOCK through shared-memory queues.  Because bvh_node::hit gives both
 //     children the un-narrowed range (PSC/bvh.h:34-35) the set of nodes/leaves a ray tests is order independent, so
-//     the (ray, node) box tests of all rays of the block are done level by level as uniform tasks (any thread takes
-//     any task), the reached (ray, leaf) pairs are collected, and then tested as uniform tasks as well; candidates
-//     are merged per ray with atomicMin on the 64-bit key.  Neither phase has per-lane control flow to diverge on.
+//     the work is cut into uniform tasks that any thread can take: a node task (ray, bvh_node whose own box passed)
+//     tests the boxes of the node's two children (64-byte record, the layout of rtnw_bvh_node) and enqueues the
+//     children that passed for the next level, leaf children go to the leaf queue untested, as in the reference;
+//     then every (ray, leaf) pair is one leaf task.  Candidates are merged per ray with atomicMin on the 64-bit key.
 #ifndef RTNW_QN
-#define RTNW_QN 3072  // capacity of each node frontier and of the leaf queue, in tasks
+#define RTNW_QN 3072  // capacity of each node frontier, in tasks
+#endif
+#ifndef RTNW_QL
+#define RTNW_QL 4096  // capacity of the leaf queue, in tasks
 #endif
 template <int BLOCK>
 struct coop_smem {
@@ -431,20 +437,22 @@ struct coop_smem {
     uint4 mkey[BLOCK];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
     hkey_t key[BLOCK];
     uint32_t q[2][RTNW_QN];
-    uint32_t ql[RTNW_QN];
+    uint32_t ql[RTNW_QL];
     int n[3];
     int nl;
+    int overflow;
 };
-#define RTNW_TASK(slot, rec) (((uint32_t)(slot) << 24) | (uint32_t)(rec))
+// task = owner slot (8 bits) | node index or leaf record (24 bits)
+#define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 24) | (uint32_t)(idx))
 
-// warp-aggregated append of up to two entries per lane: returns false for an entry that did not fit
+// warp-aggregated append of up to two entries per lane; an entry that does not fit is reported in spill0/spill1
 __device__ __forceinline__ void queue_push2(uint32_t* q, int* count, int cap, bool p0, uint32_t v0, bool p1, uint32_t v1,
                                             bool& spill0, bool& spill1) {
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned b0 = __ballot_sync(FULL, p0), b1 = __ballot_sync(FULL, p1);
     spill0 = false; spill1 = false;
-    const int total = __popc(b0) + __popc(b1);
+    const int c0 = __popc(b0), total = c0 + __popc(b1);
     if (total == 0) return;
     int base = 0;
     if (lane == 0) base = atomicAdd(count, total);
@@ -455,26 +463,34 @@ __device__ __forceinline__ void queue_push2(uint32_t* q, int* count, int cap, bo
         if (at < cap) q[at] = v0; else spill0 = true;
     }
     if (p1) {
-        const int at = base + __popc(b0) + __popc(b1 & lt);
+        const int at = base + c0 + __popc(b1 & lt);
         if (at < cap) q[at] = v1; else spill1 = true;
     }
 }
 
-// Closest hit of the block's rays against the BVH item whose root node record is `root`.  Owners have already
-// written their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Must be called by all threads.
+// Closest hit of the block's rays against the BVH item whose root is bvh_node `root` with own box [RA,RB].  Owners
+// have already written their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
 template <int BLOCK, bool COUNT>
-__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, bool active, float t_min,
-                                              uint32_t k0, uint32_t k1, trav_counters& cnt) {
+__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, float4 RA, float4 RB, bool active,
+                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt) {
     const int tid = threadIdx.x;
     if (tid < 3) sm.n[tid] = 0;
     if (tid == 3) sm.nl = 0;
+    if (tid == 4) sm.overflow = 0;
     __syncthreads();
-    {   // level 0: one task per active ray
+    {   // level 0: bvh_node::hit of the root — its own box, tested by the owner (PSC/bvh.h:31)
+        bool pass = false;
+        if (active) {
+            const float4 ro = sm.ray_o[tid], ri = sm.ray_i[tid];
+            if (COUNT) cnt.box_tests++;
+            pass = hit_aabb(RA, RB, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w);
+        }
         bool s0, s1;
-        queue_push2(sm.q[0], &sm.n[0], RTNW_QN, active, RTNW_TASK(tid, root), false, 0u, s0, s1);
+        queue_push2(sm.q[0], &sm.n[0], RTNW_QN, pass, RTNW_TASK(tid, root), false, 0u, s0, s1);
     }
     __syncthreads();
-    // ---- node phase: level-synchronous, every task is one aabb::hit
+    // ---- node phase, level-synchronous: a task = one node whose box passed; it tests its children's boxes
+#pragma unroll 1
     for (int level = 0;; ++level) {
         const int n = min(sm.n[level % 3], RTNW_QN);
         if (n == 0) break;
@@ -482,52 +498,43 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         uint32_t* nxt = sm.q[(level + 1) & 1];
         int* n_nxt = &sm.n[(level + 1) % 3];
         if (tid == 0) sm.n[(level + 2) % 3] = 0;  // consumed two levels ago, filled again at the next level
+#pragma unroll 1
         for (int base = 0; base < n; base += BLOCK) {
             const int q = base + tid;
             bool pn0 = false, pn1 = false, pl0 = false, pl1 = false;
-            uint32_t c0 = 0, c1 = 0;
-            int slot = 0;
+            int left = 0, right = 0, slot = 0;
             if (q < n) {
                 const uint32_t task = cur[q];
                 slot = (int)(task >> 24);
-                const int rec = (int)(task & 0xffffffu);
-                const float4 A = __ldg(&S.recs[rec].a), B = __ldg(&S.recs[rec].b);
+                const int node = (int)(task & 0xffffffu);
+                const float4 n0 = __ldg(&S.nodes[4 * node]), n1 = __ldg(&S.nodes[4 * node + 1]);
+                const float4 n2 = __ldg(&S.nodes[4 * node + 2]), n3 = __ldg(&S.nodes[4 * node + 3]);
                 const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
-                if (COUNT) cnt.box_tests++;
-                if (hit_aabb(A, B, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w)) {
-                    const uint32_t tag = __float_as_uint(B.z);
-                    c0 = RTNW_TASK(slot, rec + 1);
-                    c1 = RTNW_TASK(slot, rec + (int)(tag >> 8));
-                    const bool has_r = !(tag & RTNW_NODE_RNONE);
-                    pl0 = (tag & RTNW_NODE_LLEAF) != 0; pn0 = !pl0;
-                    pl1 = has_r && (tag & RTNW_NODE_RLEAF) != 0; pn1 = has_r && !pl1;
+                const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
+                left = __float_as_int(n0.w); right = __float_as_int(n1.w);
+                if (left >= 0) {
+                    if (COUNT) cnt.box_tests++;
+                    pn0 = hit_aabb(make_float4(n0.x, n0.y, n0.z, n1.x), make_float4(n1.y, n1.z, 0.f, 0.f), o, inv, t_min, ro.w);
+                } else {
+                    pl0 = true;  // leaves are handed the ray without a box test (PSC/bvh.h:34)
+                }
+                if (right >= 0) {
+                    if (COUNT) cnt.box_tests++;
+                    pn1 = hit_aabb(make_float4(n2.x, n2.y, n2.z, n3.x), make_float4(n3.y, n3.z, 0.f, 0.f), o, inv, t_min, ro.w);
+                } else {
+                    pl1 = right != RTNW_REF_NONE;
                 }
             }
             bool sn0, sn1, sl0, sl1;
-            queue_push2(nxt, n_nxt, RTNW_QN, pn0, c0, pn1, c1, sn0, sn1);
-            queue_push2(sm.ql, &sm.nl, RTNW_QN, pl0, c0, pl1, c1, sl0, sl1);
-            if (sn0 | sn1 | sl0 | sl1) {  // a queue is full: finish those children right here, sequentially
-                const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
-                const uint4 mq = sm.mkey[slot];
-                ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
-                medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-                hkey_t best = RTNW_KEY_NONE;
-                for (int w = 0; w < 2; ++w) {
-                    const bool sp = w ? (sn1 | sl1) : (sn0 | sl0);
-                    if (!sp) continue;
-                    const int c = (int)((w ? c1 : c0) & 0xffffffu);
-                    const bool is_node = w ? sn1 : sn0;
-                    const int end = is_node ? __float_as_int(__ldg(&S.recs[c].b).w) : c + 1;
-                    const hkey_t k = subtree_closest<COUNT>(S, c, is_node ? end : c + 1, r, mk3(ri.x, ri.y, ri.z), rd.w, t_min, ro.w, mk);
-                    if (k < best) best = k;
-                }
-                if (best != RTNW_KEY_NONE) atomicMin(&sm.key[slot], best);
-            }
+            queue_push2(nxt, n_nxt, RTNW_QN, pn0, RTNW_TASK(slot, left), pn1, RTNW_TASK(slot, right), sn0, sn1);
+            queue_push2(sm.ql, &sm.nl, RTNW_QL, pl0, RTNW_TASK(slot, ~left), pl1, RTNW_TASK(slot, ~right), sl0, sl1);
+            if (sn0 | sn1 | sl0 | sl1) sm.overflow = 1;  // a queue is full: the item is redone sequentially below
         }
         __syncthreads();
     }
     // ---- leaf phase: every task is one leaf->hit(r, tmin, tmax0)
-    const int nl = min(sm.nl, RTNW_QN);
+    const int nl = min(sm.nl, RTNW_QL);
+#pragma unroll 1
     for (int q = tid; q < nl; q += BLOCK) {
         const uint32_t task = sm.ql[q];
         const int slot = (int)(task >> 24), rec = (int)(task & 0xffffffu);
@@ -539,6 +546,22 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
     }
     __syncthreads();
+    if (sm.overflow) {
+        // Some task did not fit a queue (frontier wider than RTNW_QN / more than RTNW_QL leaves for this block's rays):
+        // every owner walks the whole tree for its own ray.  Leaves already tested are merely tested again — the key
+        // minimum is idempotent — so the result is the same as if the queues had been large enough.
+        if (active) {
+            const float4 ro = sm.ray_o[tid], rd = sm.ray_d[tid], ri = sm.ray_i[tid];
+            if (hit_aabb(RA, RB, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w)) {
+                const uint4 mq = sm.mkey[tid];
+                ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+                medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
+                const hkey_t k = subtree_closest<COUNT>(S, root, r, mk3(ri.x, ri.y, ri.z), rd.w, t_min, ro.w, mk);
+                if (k != RTNW_KEY_NONE) atomicMin(&sm.key[tid], k);
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
@@ -564,9 +587,11 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
             sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
             sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
             sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-            coop_bvh_item<BLOCK, COUNT>(S, sm, i + 1, active, t_min, mk.k0, mk.k1, cnt);
+            const float4 RA = __ldg(&S.recs[i + 1].a), RB = __ldg(&S.recs[i + 1].b);  // the root bvh_node's own box
+            coop_bvh_item<BLOCK, COUNT>(S, sm, __float_as_int(IA.y), RA, RB, active, t_min, mk.k0, mk.k1, cnt);
         } else if (active) {
             float lim = best_t;
+#pragma unroll 1
             for (int j = i + 1; j < next;) {
                 const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
                 bool hit; float t; int face;
@@ -686,6 +711,7 @@ __device__ __forceinline__ float perlin_noise(const scene_view& S, f3 p) {
 __device__ __forceinline__ float perlin_turb(const scene_view& S, f3 p) {
     float accum = 0.f, weight = 1.0f;
     f3 q = p;
+#pragma unroll 1
     for (int o = 0; o < 7; ++o) {
         accum += weight * perlin_noise(S, q);
         weight *= 0.5f;

@@ -1,6 +1,6 @@
 """Philox4x32-10 in numpy: the framework's counter-based stream, for tests only.
 
-sequential draw n of path (pixel, sample): block = philox(ctr=(n>>2, 0, sample, pixel), key=seed), value = block[n&3]
+sequential stream of path (pixel, sample): philox(ctr=(0, 0, sample, pixel), key=seed) seeds the drand48 recurrence
 keyed medium draw:                         philox(ctr=(leaf, 1+depth, sample, pixel), key=seed)[0]
 u01(x) = float32(x >> 8) * 2^-24
 """
@@ -32,10 +32,13 @@ def u01(x):
 
 
 def seq_draws(seed, pixel, sample, n):
-    """first n sequential draws of one path as float32"""
-    out = []
+    """first n sequential draws of one path as float32: Philox(0, 0, sample, pixel) seeds the drand48 recurrence
+    X <- (0x5DEECE66D X + 0xB) mod 2^48, a draw is the top 24 bits of X"""
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    for blk in range((n + 3) // 4):
-        b = philox4x32_10((blk, 0, sample, pixel), key)
-        out.extend(float(u01(v)) for v in b)
-    return np.array(out[:n], dtype=np.float32)
+    b = philox4x32_10((0, 0, sample, pixel), key)
+    x = ((int(b[1]) & 0xFFFF) << 32) | int(b[0])
+    out = []
+    for _ in range(n):
+        x = (x * 0x5DEECE66D + 0xB) & 0xFFFFFFFFFFFF
+        out.append(np.float32(x >> 24) * np.float32(1.0 / 16777216.0))
+    return np.array(out, dtype=np.float32)
