@@ -29,7 +29,7 @@ struct render_args {
     rtnw_camera cam;
     rtnw_render_params p;
     float* accum;                 // nx*ny*3 sums, index (j*nx+i)*3+c
-    unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests
+    unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests, [4] task stack overflows
 };
 
 typedef coop_smem<RTNW_BLOCK> block_smem;
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
     const bool sky = P.p.background == RTNW_BG_SKY;
 
+    if (threadIdx.x == 0) sm.overflow = 0;
     bool alive = true, need = true;
     int pix = -1, k = 0, depth = 0;
     f3 col = mk3(0.f, 0.f, 0.f), L = col, T = col;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             }
         }
     }
+    if (threadIdx.x == 0 && sm.overflow) atomicAdd(&P.ctr[4], 1ull);
     // work counters: one atomic per warp
     if (COUNT) { box_total = cnt.box_tests; prim_total = cnt.prim_tests; }
     for (int o = 16; o > 0; o >>= 1) n_rays += __shfl_xor_sync(FULL, n_rays, o);
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     mk.k0 = (uint32_t)seed; mk.k1 = (uint32_t)(seed >> 32); mk.pixel = in.key; mk.sample = 0; mk.depth = 0;
     trav_counters cnt;
     cnt.box_tests = 0; cnt.prim_tests = 0;
+    if (threadIdx.x == 0) sm.overflow = 0;
     const hkey_t key = coop_closest_hit<RTNW_BLOCK, false>(S, sm, r, active, t_min, t_max, mk, cnt);
     if (!active) return;
     hit_t h;
@@ -403,7 +406,7 @@ struct stream_builder {
     // it), the node itself goes to the two-box table with its leaf children rewritten to record indices.
     bool emit_node(int32_t idx, int depth) {
         if (idx < 0 || idx >= d.n_nodes) return bad("BVH node index out of range");
-        if (depth >= 60) return bad("BVH deeper than 60 levels");
+        if (depth >= RTNW_QN / RTNW_BLOCK - 1) return bad("BVH deeper than the cooperative task stack allows (RTNW_QN / RTNW_BLOCK - 1 levels)");
         if (node_seen[idx]) return bad("BVH node referenced twice");
         node_seen[idx] = 1;
         const rtnw_bvh_node& n = d.nodes[idx];
@@ -530,14 +533,15 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     a.p = *p;
     a.accum = accum_dev;
     a.ctr = ctx->ctr;
-    CUDA_TRY(cudaMemsetAsync(ctx->ctr, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(ctx->ctr, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(ctx->ev0, st));
     const int rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true>(ctx, a, st) : launch_render<false>(ctx, a, st);
     if (rc != RTNW_OK) return rc;
     CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-    unsigned long long h[4];
+    unsigned long long h[8];
     CUDA_TRY(cudaMemcpyAsync(h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (h[4]) return fail(RTNW_ERR_UNSUPPORTED, "BVH task stack overflow: the tree is deeper than RTNW_QN/RTNW_BLOCK - 1 levels");
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         stats->paths = (uint64_t)p->nx * p->ny * p->sample_count;
@@ -590,7 +594,7 @@ int rtnw_ctx_create(int device, rtnw_ctx** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e == cudaSuccess) e = cudaMalloc(&c->ctr, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->ctr, 8 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         rtnw_ctx_destroy(c);
         return fail(RTNW_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));

@@ -382,52 +382,23 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
     return best;
 }
 
-// Sequential closest hit below one bvh_node whose own box already passed (used when a shared-memory queue is full;
-// same result as the cooperative traversal because the set of leaves a ray tests does not depend on the order).
-template <bool COUNT>
-__device__ __noinline__ hkey_t subtree_closest(const scene_view& S, int node, ray_t r, f3 inv, float a, float t_min, float tmax0,
-                                               medium_key mk) {
-    hkey_t best = RTNW_KEY_NONE;
-    trav_counters cnt;
-    cnt.box_tests = 0; cnt.prim_tests = 0;
-    int stack[64];  // depth is validated at upload
-    int sp = 0;
-    stack[sp++] = node;
-    while (sp > 0) {
-        const int n = stack[--sp];
-        const float4 n0 = __ldg(&S.nodes[4 * n]), n1 = __ldg(&S.nodes[4 * n + 1]);
-        const float4 n2 = __ldg(&S.nodes[4 * n + 2]), n3 = __ldg(&S.nodes[4 * n + 3]);
-        const int left = __float_as_int(n0.w), right = __float_as_int(n1.w);
-        for (int w = 0; w < 2; ++w) {
-            const int c = w ? right : left;
-            if (c == RTNW_REF_NONE) continue;
-            if (c >= 0) {
-                const float4 lo = w ? n2 : n0, hi = w ? n3 : n1;
-                if (hit_aabb(make_float4(lo.x, lo.y, lo.z, hi.x), make_float4(hi.y, hi.z, 0.f, 0.f), r.o, inv, t_min, tmax0) && sp < 64)
-                    stack[sp++] = c;
-            } else {
-                const hkey_t k = test_leaf<COUNT>(S, ~c, r, a, t_min, tmax0, mk, cnt);
-                if (k < best) best = k;
-            }
-        }
-    }
-    return best;
-}
-
 // ---- block-cooperative closest hit --------------------------------------------------------------------------
 // Every thread of the block owns one ray (or none).  All rays walk the same record stream, item by item:
 //   * a list item (PSC/hitable_list.h:20-32) is scanned by each owner in lockstep: same records, same code, all lanes;
-//   * a BVH item is traversed by the WHOLE BLOCK through shared-memory queues.  Because bvh_node::hit gives both
+//   * a BVH item is traversed by the WHOLE BLOCK through a shared-memory task stack.  Because bvh_node::hit gives both
 //     children the un-narrowed range (PSC/bvh.h:34-35) the set of nodes/leaves a ray tests is order independent, so
 //     the work is cut into uniform tasks that any thread can take: a node task (ray, bvh_node whose own box passed)
-//     tests the boxes of the node's two children (64-byte record, the layout of rtnw_bvh_node) and enqueues the
-//     children that passed for the next level, leaf children go to the leaf queue untested, as in the reference;
-//     then every (ray, leaf) pair is one leaf task.  Candidates are merged per ray with atomicMin on the 64-bit key.
+//     tests the boxes of the node's two children (64-byte record, the layout of rtnw_bvh_node) and pushes the children
+//     that passed; leaf children go to the leaf queue untested, as in the reference; every (ray, leaf) pair is one
+//     leaf task.  Candidates are merged per ray with atomicMin on the 64-bit key.
+//     The stack is served LIFO, BLOCK tasks at a time: each round pops at most BLOCK tasks and pushes at most 2*BLOCK
+//     children one level deeper, so it never holds more than BLOCK*(depth+1) tasks (depth is validated at upload),
+//     and every round but the last few runs with all threads busy.
 #ifndef RTNW_QN
-#define RTNW_QN 3072  // capacity of each node frontier, in tasks
+#define RTNW_QN 3072  // node task stack: room for trees of depth <= RTNW_QN/BLOCK - 1
 #endif
 #ifndef RTNW_QL
-#define RTNW_QL 4096  // capacity of the leaf queue, in tasks
+#define RTNW_QL 2048  // leaf queue; flushed whenever fewer than 2*BLOCK slots are free
 #endif
 template <int BLOCK>
 struct coop_smem {
@@ -436,103 +407,43 @@ struct coop_smem {
     float4 ray_i[BLOCK];  // 1/d, w = time
     uint4 mkey[BLOCK];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
     hkey_t key[BLOCK];
-    uint32_t q[2][RTNW_QN];
+    uint32_t q[RTNW_QN];
     uint32_t ql[RTNW_QL];
-    int n[3];
+    int n[2];             // stack height, double-buffered across rounds
     int nl;
-    int overflow;
+    int overflow;         // a push did not fit (cannot happen for validated scenes); reported to the host
 };
 // task = owner slot (8 bits) | node index or leaf record (24 bits)
 #define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 24) | (uint32_t)(idx))
 
-// warp-aggregated append of up to two entries per lane; an entry that does not fit is reported in spill0/spill1
-__device__ __forceinline__ void queue_push2(uint32_t* q, int* count, int cap, bool p0, uint32_t v0, bool p1, uint32_t v1,
-                                            bool& spill0, bool& spill1) {
+// warp-aggregated append of up to two entries per lane; returns false if an entry did not fit
+__device__ __forceinline__ bool queue_push2(uint32_t* q, int* count, int cap, bool p0, uint32_t v0, bool p1, uint32_t v1) {
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned b0 = __ballot_sync(FULL, p0), b1 = __ballot_sync(FULL, p1);
-    spill0 = false; spill1 = false;
     const int c0 = __popc(b0), total = c0 + __popc(b1);
-    if (total == 0) return;
+    if (total == 0) return true;
     int base = 0;
     if (lane == 0) base = atomicAdd(count, total);
     base = __shfl_sync(FULL, base, 0);
     const unsigned lt = (1u << lane) - 1u;
+    bool ok = true;
     if (p0) {
         const int at = base + __popc(b0 & lt);
-        if (at < cap) q[at] = v0; else spill0 = true;
+        if (at < cap) q[at] = v0; else ok = false;
     }
     if (p1) {
         const int at = base + c0 + __popc(b1 & lt);
-        if (at < cap) q[at] = v1; else spill1 = true;
+        if (at < cap) q[at] = v1; else ok = false;
     }
+    return ok;
 }
 
-// Closest hit of the block's rays against the BVH item whose root is bvh_node `root` with own box [RA,RB].  Owners
-// have already written their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
+// every queued (ray, leaf) pair is one leaf->hit(r, tmin, tmax0); all threads, then the queue is empty again
 template <int BLOCK, bool COUNT>
-__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, float4 RA, float4 RB, bool active,
-                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt) {
+__device__ __forceinline__ void coop_flush_leaves(const scene_view& S, coop_smem<BLOCK>& sm, float t_min, uint32_t k0, uint32_t k1,
+                                                  trav_counters& cnt) {
     const int tid = threadIdx.x;
-    if (tid < 3) sm.n[tid] = 0;
-    if (tid == 3) sm.nl = 0;
-    if (tid == 4) sm.overflow = 0;
-    __syncthreads();
-    {   // level 0: bvh_node::hit of the root — its own box, tested by the owner (PSC/bvh.h:31)
-        bool pass = false;
-        if (active) {
-            const float4 ro = sm.ray_o[tid], ri = sm.ray_i[tid];
-            if (COUNT) cnt.box_tests++;
-            pass = hit_aabb(RA, RB, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w);
-        }
-        bool s0, s1;
-        queue_push2(sm.q[0], &sm.n[0], RTNW_QN, pass, RTNW_TASK(tid, root), false, 0u, s0, s1);
-    }
-    __syncthreads();
-    // ---- node phase, level-synchronous: a task = one node whose box passed; it tests its children's boxes
-#pragma unroll 1
-    for (int level = 0;; ++level) {
-        const int n = min(sm.n[level % 3], RTNW_QN);
-        if (n == 0) break;
-        const uint32_t* cur = sm.q[level & 1];
-        uint32_t* nxt = sm.q[(level + 1) & 1];
-        int* n_nxt = &sm.n[(level + 1) % 3];
-        if (tid == 0) sm.n[(level + 2) % 3] = 0;  // consumed two levels ago, filled again at the next level
-#pragma unroll 1
-        for (int base = 0; base < n; base += BLOCK) {
-            const int q = base + tid;
-            bool pn0 = false, pn1 = false, pl0 = false, pl1 = false;
-            int left = 0, right = 0, slot = 0;
-            if (q < n) {
-                const uint32_t task = cur[q];
-                slot = (int)(task >> 24);
-                const int node = (int)(task & 0xffffffu);
-                const float4 n0 = __ldg(&S.nodes[4 * node]), n1 = __ldg(&S.nodes[4 * node + 1]);
-                const float4 n2 = __ldg(&S.nodes[4 * node + 2]), n3 = __ldg(&S.nodes[4 * node + 3]);
-                const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
-                const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
-                left = __float_as_int(n0.w); right = __float_as_int(n1.w);
-                if (left >= 0) {
-                    if (COUNT) cnt.box_tests++;
-                    pn0 = hit_aabb(make_float4(n0.x, n0.y, n0.z, n1.x), make_float4(n1.y, n1.z, 0.f, 0.f), o, inv, t_min, ro.w);
-                } else {
-                    pl0 = true;  // leaves are handed the ray without a box test (PSC/bvh.h:34)
-                }
-                if (right >= 0) {
-                    if (COUNT) cnt.box_tests++;
-                    pn1 = hit_aabb(make_float4(n2.x, n2.y, n2.z, n3.x), make_float4(n3.y, n3.z, 0.f, 0.f), o, inv, t_min, ro.w);
-                } else {
-                    pl1 = right != RTNW_REF_NONE;
-                }
-            }
-            bool sn0, sn1, sl0, sl1;
-            queue_push2(nxt, n_nxt, RTNW_QN, pn0, RTNW_TASK(slot, left), pn1, RTNW_TASK(slot, right), sn0, sn1);
-            queue_push2(sm.ql, &sm.nl, RTNW_QL, pl0, RTNW_TASK(slot, ~left), pl1, RTNW_TASK(slot, ~right), sl0, sl1);
-            if (sn0 | sn1 | sl0 | sl1) sm.overflow = 1;  // a queue is full: the item is redone sequentially below
-        }
-        __syncthreads();
-    }
-    // ---- leaf phase: every task is one leaf->hit(r, tmin, tmax0)
     const int nl = min(sm.nl, RTNW_QL);
 #pragma unroll 1
     for (int q = tid; q < nl; q += BLOCK) {
@@ -546,22 +457,70 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
     }
     __syncthreads();
-    if (sm.overflow) {
-        // Some task did not fit a queue (frontier wider than RTNW_QN / more than RTNW_QL leaves for this block's rays):
-        // every owner walks the whole tree for its own ray.  Leaves already tested are merely tested again — the key
-        // minimum is idempotent — so the result is the same as if the queues had been large enough.
+    if (tid == 0) sm.nl = 0;
+    __syncthreads();
+}
+
+// Closest hit of the block's rays against the BVH item whose root is bvh_node `root` with own box [RA,RB].  Owners
+// have already written their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
+template <int BLOCK, bool COUNT>
+__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, float4 RA, float4 RB, bool active,
+                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt) {
+    const int tid = threadIdx.x;
+    if (tid < 2) sm.n[tid] = 0;
+    if (tid == 2) sm.nl = 0;
+    __syncthreads();
+    {   // bvh_node::hit of the root: its own box, tested by the owner (PSC/bvh.h:31)
+        bool pass = false;
         if (active) {
-            const float4 ro = sm.ray_o[tid], rd = sm.ray_d[tid], ri = sm.ray_i[tid];
-            if (hit_aabb(RA, RB, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w)) {
-                const uint4 mq = sm.mkey[tid];
-                ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
-                medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-                const hkey_t k = subtree_closest<COUNT>(S, root, r, mk3(ri.x, ri.y, ri.z), rd.w, t_min, ro.w, mk);
-                if (k != RTNW_KEY_NONE) atomicMin(&sm.key[tid], k);
+            const float4 ro = sm.ray_o[tid], ri = sm.ray_i[tid];
+            if (COUNT) cnt.box_tests++;
+            pass = hit_aabb(RA, RB, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w);
+        }
+        queue_push2(sm.q, &sm.n[0], RTNW_QN, pass, RTNW_TASK(tid, root), false, 0u);
+    }
+    __syncthreads();
+    // ---- node rounds: a task = one node whose box passed; it tests its children's boxes
+#pragma unroll 1
+    for (int round = 0;; ++round) {
+        const int n = sm.n[round & 1];
+        if (n == 0) break;
+        const int take = min(n, BLOCK), base = n - take;
+        int* n_nxt = &sm.n[(round + 1) & 1];
+        uint32_t task = 0;
+        if (tid < take) task = sm.q[base + tid];
+        if (tid == 0) *n_nxt = base;  // pop; this round's pushes land on top of what remains
+        __syncthreads();
+        bool pn0 = false, pn1 = false, pl0 = false, pl1 = false;
+        int left = 0, right = 0;
+        const int slot = (int)(task >> 24);
+        if (tid < take) {
+            const int node = (int)(task & 0xffffffu);
+            const float4 n0 = __ldg(&S.nodes[4 * node]), n1 = __ldg(&S.nodes[4 * node + 1]);
+            const float4 n2 = __ldg(&S.nodes[4 * node + 2]), n3 = __ldg(&S.nodes[4 * node + 3]);
+            const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
+            const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
+            left = __float_as_int(n0.w); right = __float_as_int(n1.w);
+            if (left >= 0) {
+                if (COUNT) cnt.box_tests++;
+                pn0 = hit_aabb(make_float4(n0.x, n0.y, n0.z, n1.x), make_float4(n1.y, n1.z, 0.f, 0.f), o, inv, t_min, ro.w);
+            } else {
+                pl0 = true;  // leaves are handed the ray without a box test (PSC/bvh.h:34)
+            }
+            if (right >= 0) {
+                if (COUNT) cnt.box_tests++;
+                pn1 = hit_aabb(make_float4(n2.x, n2.y, n2.z, n3.x), make_float4(n3.y, n3.z, 0.f, 0.f), o, inv, t_min, ro.w);
+            } else {
+                pl1 = right != RTNW_REF_NONE;
             }
         }
+        const bool ok_n = queue_push2(sm.q, n_nxt, RTNW_QN, pn0, RTNW_TASK(slot, left), pn1, RTNW_TASK(slot, right));
+        const bool ok_l = queue_push2(sm.ql, &sm.nl, RTNW_QL, pl0, RTNW_TASK(slot, ~left), pl1, RTNW_TASK(slot, ~right));
+        if (!(ok_n && ok_l)) sm.overflow = 1;
         __syncthreads();
+        if (sm.nl > RTNW_QL - 2 * BLOCK) coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
     }
+    coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
 }
 
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
