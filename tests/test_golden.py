@@ -1,0 +1,110 @@
+"""Golden fixtures (tests/golden/*.npz, generated from the reference itself by tests/golden/make_golden.py):
+  * CPU: the C restatement of the oracle reproduces every fixture bit for bit (no reference needed at run time);
+  * GPU: the CUDA path, through the C-ABI, reproduces ids / t / p / normal bit for bit, uv within 1e-5, and the
+    sample-for-sample renders within the tolerance of test_gpu_parity.py."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_port as op
+from raysets import FLT_MAX, assert_hits_equal
+
+GOLD = Path(__file__).resolve().parent / "golden"
+TRACE = sorted(p.stem[len("trace_"):] for p in GOLD.glob("trace_*.npz"))
+RENDER = sorted(p.stem[len("render_"):] for p in GOLD.glob("render_*.npz"))
+
+
+def scene_name(stem):
+    return stem[:-4] + "+bvh" if stem.endswith("_bvh") else stem
+
+
+def test_fixtures_are_present():
+    assert len(TRACE) >= 10 and len(RENDER) >= 9 and (GOLD / "units.npz").exists()
+
+
+@pytest.mark.parametrize("stem", TRACE)
+def test_oracle_port_reproduces_golden_hits(rtnw, stem):
+    g = np.load(GOLD / f"trace_{stem}.npz")
+    hs = rtnw.HostScene(scene_name(stem))
+    seed = int(g["seed"])
+    assert_hits_equal(op.trace(rtnw, hs.desc_ptr, g["rays"], 0.001, FLT_MAX, seed=seed), g["hits_a"], uv_tol=0)
+    assert_hits_equal(op.trace(rtnw, hs.desc_ptr, g["rays"], 0.0, 400.0, seed=seed), g["hits_b"], uv_tol=0)
+
+
+@pytest.mark.parametrize("stem", RENDER)
+def test_oracle_port_reproduces_golden_renders(rtnw, stem):
+    g = np.load(GOLD / f"render_{stem}.npz")
+    hs = rtnw.HostScene(scene_name(stem))
+    nx, ny, ns = int(g["nx"]), int(g["ny"]), int(g["ns"])
+    got, st = op.render(rtnw, hs.desc_ptr, hs.camera(nx, ny), hs.params(nx=nx, ny=ny, ns=ns, seed=int(g["seed"])))
+    assert np.array_equal(got.view(np.uint32), g["sums"].view(np.uint32))
+    assert st["rays"] == float(g["rays"])
+
+
+def test_oracle_port_reproduces_golden_units(rtnw):
+    g = np.load(GOLD / "units.npz")
+    hs = rtnw.HostScene("two_perlin")
+    d = hs.desc
+    kinds = [d.textures[i].kind for i in range(d.n_textures)]
+    assert np.array_equal(op.eval_perlin(rtnw, hs.desc_ptr, 0, g["xyz"]), g["noise"])
+    assert np.array_equal(op.eval_perlin(rtnw, hs.desc_ptr, 1, g["xyz"]), g["turb"])
+    assert np.array_equal(op.eval_texture(rtnw, hs.desc_ptr, kinds.index(1), g["uvp"]), g["checker"])
+    assert np.array_equal(op.eval_texture(rtnw, hs.desc_ptr, kinds.index(2), g["uvp"]), g["noise_tex"])
+    he = rtnw.HostScene("earth")
+    ke = [he.desc.textures[i].kind for i in range(he.desc.n_textures)]
+    assert np.array_equal(op.eval_texture(rtnw, he.desc_ptr, ke.index(3), g["uvp"]), g["image"])
+    cam = rtnw.HostScene("ch01_random").camera(200, 100)
+    got = op.camera_rays(rtnw, cam, 200, 100, g["cam_ij"], g["cam_sample"], seed=77)
+    for f in ("origin", "direction", "time", "key"):
+        assert np.array_equal(got[f], g["cam_rays"][f]), f
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem", TRACE)
+def test_cuda_reproduces_golden_hits(rtnw, ctx, stem):
+    g = np.load(GOLD / f"trace_{stem}.npz")
+    hs = rtnw.HostScene(scene_name(stem))
+    ds = ctx.upload(hs.desc_ptr)
+    seed = int(g["seed"])
+    assert_hits_equal(ds.trace(g["rays"], 0.001, FLT_MAX, seed=seed), g["hits_a"])
+    assert_hits_equal(ds.trace(g["rays"], 0.0, 400.0, seed=seed), g["hits_b"])
+    ds.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem", RENDER)
+def test_cuda_reproduces_golden_renders(rtnw, ctx, stem):
+    g = np.load(GOLD / f"render_{stem}.npz")
+    hs = rtnw.HostScene(scene_name(stem))
+    ds = ctx.upload(hs.desc_ptr)
+    nx, ny, ns = int(g["nx"]), int(g["ny"]), int(g["ns"])
+    got, st = ds.render(hs.camera(nx, ny), hs.params(nx=nx, ny=ny, ns=ns, seed=int(g["seed"])))
+    close = np.isclose(got, g["sums"], rtol=2e-5, atol=1e-6).all(axis=2)
+    assert close.mean() >= 0.99, f"{stem}: only {close.mean():.4f} of pixels agree with the reference"
+    assert abs(st.rays - float(g["rays"])) <= 0.003 * float(g["rays"])
+    ds.close()
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_units(rtnw, ctx):
+    g = np.load(GOLD / "units.npz")
+    hs = rtnw.HostScene("two_perlin")
+    ds = ctx.upload(hs.desc_ptr)
+    d = hs.desc
+    kinds = [d.textures[i].kind for i in range(d.n_textures)]
+    assert np.array_equal(ds.eval_perlin(0, g["xyz"]), g["noise"])
+    assert np.array_equal(ds.eval_perlin(1, g["xyz"]), g["turb"])
+    assert (np.all(ds.eval_texture(kinds.index(1), g["uvp"]) == g["checker"], axis=1)).mean() > 0.998
+    assert np.allclose(ds.eval_texture(kinds.index(2), g["uvp"]), g["noise_tex"], rtol=0, atol=2e-6)
+    ds.close()
+    he = rtnw.HostScene("earth")
+    de = ctx.upload(he.desc_ptr)
+    ke = [he.desc.textures[i].kind for i in range(he.desc.n_textures)]
+    assert np.array_equal(de.eval_texture(ke.index(3), g["uvp"]), g["image"])
+    de.close()
+    cam = rtnw.HostScene("ch01_random").camera(200, 100)
+    got = rtnw.camera_rays(ctx, cam, 200, 100, g["cam_ij"], g["cam_sample"], seed=77)
+    for f in ("origin", "direction", "time", "key"):
+        assert np.array_equal(got[f], g["cam_rays"][f]), f
