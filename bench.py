@@ -31,8 +31,9 @@ SEED = 20181025
 # sphere, 10/rect, 60/medium, +100 shading (+800 per noise_texture hit, +60 per checker hit).
 F_OPS = dict(aabb=18.0, sphere=25.0, moving_sphere=30.0, rect=10.0, medium=60.0, shade=100.0)
 # per-ray test counts of config 5N measured with the reference's own counters (oracle/ref_harness.cpp ref_cnt) at
-# 200x200x16; refreshed from the live cpu_baseline leg when it runs.  See DESIGN.md §7.
-DEFAULT_COUNTS = dict(aabb=52.4, sphere=8.6, moving_sphere=1.0, rect=10.6, medium=2.0)
+# 200x200x4 (sphere/rect counts include media boundaries and box faces); refreshed from the live cpu_baseline leg when
+# it runs.  See DESIGN.md §7.
+DEFAULT_COUNTS = dict(aabb=24.13, sphere=9.96, moving_sphere=1.0, rect=19.49, medium=2.0)
 
 
 def flops_per_ray(c):
@@ -79,9 +80,10 @@ def reference_main(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_oracle.so was not built"}))
         return 0
     procs = os.cpu_count() or 1
-    # bounded sample of the workload: same scene and camera, 200x200 pixels, `procs` samples per pixel per step
+    # bounded sample of the workload: same scene and camera, 200x200 pixels, 24 samples per pixel per process and step
+    # (about 6 s of CPU work per step at ~160 kpaths/s per core)
     nx = ny = 200
-    ns = max(procs, 8)
+    ns = 24 * procs
     times, paths, rays = [], 0, 0
     for it in range(args.warmup + args.steps):
         r = run_reference(WORKLOAD["scene"], nx, ny, ns, procs)
@@ -158,6 +160,7 @@ def main():
     import numpy as np
     import torch
     rtnw = importlib.import_module("peter-shirley-ray-tracing-the-next-week_b200")
+    mg = importlib.import_module("peter-shirley-ray-tracing-the-next-week_b200.multi_gpu")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,8 +180,8 @@ def main():
     ds = ctx.upload(hs.desc_ptr)
     nx, ny, ns = WORKLOAD["nx"], WORKLOAD["ny"], WORKLOAD["ns"]
     cam = hs.camera(nx, ny)
-    my_ns = len(range(rank, ns, world))  # samples rank, rank+world, ...
-    params = hs.params(nx=nx, ny=ny, ns=my_ns, seed=SEED, sample_begin=rank, sample_stride=world, flags_extra=args.flags)
+    begin, my_ns, stride = mg.sample_partition(ns, world, rank)  # samples rank, rank+world, ...
+    params = hs.params(nx=nx, ny=ny, ns=my_ns, seed=SEED, sample_begin=begin, sample_stride=stride, flags_extra=args.flags)
     accum = torch.empty(ny, nx, 3, dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
@@ -188,11 +191,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = {}
+
     def step():
-        st = ds.render_device(cam, params, accum.data_ptr(), stream.cuda_stream)
-        if dist is not None:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-        return st
+        def render(b, c, s):
+            last["st"] = ds.render_device(cam, params, accum.data_ptr(), stream.cuda_stream)
+        mg.render_partitioned(render, accum, ns, dist=dist, dst=0)  # k_render on every rank, then one NCCL reduce(sum)
+        return last["st"]
 
     for _ in range(args.warmup):
         step()
@@ -228,12 +233,16 @@ def main():
     host_accum = torch.empty(ny, nx, 3, dtype=torch.float32).pin_memory()
     host_np = host_accum.numpy()
 
+    e2e_kernel_ms = []
+
     def e2e_step():
         s2 = ctx.upload(hs.desc_ptr)  # H2D of every scene table
         if dist is None:
-            s2.render(cam, params, out=host_np)  # render + D2H into pinned host memory
+            _, st2 = s2.render(cam, params, out=host_np)  # render + D2H into pinned host memory
+            e2e_kernel_ms.append(st2.kernel_ms)
         else:
-            s2.render_device(cam, params, accum.data_ptr(), stream.cuda_stream)
+            st2 = s2.render_device(cam, params, accum.data_ptr(), stream.cuda_stream)
+            e2e_kernel_ms.append(st2.kernel_ms)
             dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 host_accum.copy_(accum, non_blocking=False)
@@ -258,11 +267,11 @@ def main():
         import ref_oracle as ro
         if ro.available():
             procs = os.cpu_count() or 1
-            r = run_reference(WORKLOAD["scene"], 200, 200, max(procs, 8) * 2, procs)
+            r = run_reference(WORKLOAD["scene"], 200, 200, 64 * procs, procs)  # ~16 s of CPU work per core
             counts = r["counts"]
             cpu = {"value": r["paths"] / r["seconds"] / 1e6, "unit": "Mpaths/s", "cores": procs, "kind": "reference",
                    "mrays_per_s": r["rays"] / r["seconds"] / 1e6,
-                   "sample": f"200x200 pixels x {max(procs, 8) * 2} spp of the same scene/camera, {procs} processes "
+                   "sample": f"200x200 pixels x {64 * procs} spp of the same scene/camera, {procs} processes "
                              f"(the reference is single-threaded), glibc drand48; {r['seconds']:.1f} s"}
     if rank == 0:
         peaks = {}
@@ -275,7 +284,8 @@ def main():
         rays_per_launch = rays / args.steps
         f_ray = flops_per_ray(counts)
         sm_mhz = clocks["sm_mhz"] or (info["clock_khz"] / 1e3)
-        fp32_peak = info["sm_count"] * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load (FMA = 2)
+        fp32_nominal = info["sm_count"] * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load (FMA = 2)
+        fp32_peak = ctx.fp32_peak_tflops()  # measured on this device: independent FFMA chains (rtnw_measure_fp32_peak)
         achieved = rays_per_launch * f_ray / kernel_s / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_bytes = nx * ny * 3 * 4 + desc_bytes
@@ -290,12 +300,15 @@ def main():
                        "seed": SEED},
             "mrays_per_s": mrays, "rays_per_path": tot_rays.item() / (paths_per_step * args.steps),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": desc_bytes * world,
-                    "d2h_bytes_per_step": nx * ny * 3 * 4},
+                    "d2h_bytes_per_step": nx * ny * 3 * 4, "ms_per_step": 1e3 * e2e_s.item() / args.steps,
+                    "kernel_ms_per_step": sum(e2e_kernel_ms[-args.steps:]) / args.steps},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "traffic": None, "kernel": "k_render", "kernel_ms": 1e3 * kernel_s, "flop_per_ray": f_ray,
-                         "peak_source": f"{info['sm_count']} SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock under load)",
+                         "peak_source": f"measured FFMA microbenchmark on this GPU (nominal {fp32_nominal:.1f} = {info['sm_count']} SM x "
+                                        f"128 lanes x 2 x {sm_mhz:.0f} MHz)",
+                         "note": "FP32-issue bound, not HBM/tensor: the scene (<2 MB) lives in L1/L2; see the hbm sub-object",
                          "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak, "algorithmic_bytes": hbm_bytes,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

@@ -153,8 +153,8 @@ enum rtnw_background { RTNW_BG_BLACK = 0 /* PSC/main.cpp:44 */, RTNW_BG_SKY = 1 
 /* render flags */
 #define RTNW_F_DE_NAN        1u  /* per-sample NaN->0, PSC/main.cpp:232-242,311 */
 #define RTNW_F_EMIT          2u  /* add material emitted(), PSC/main.cpp:33 (off only for the Ch01/Ch03 snapshots) */
-#define RTNW_F_CULL_NARROW   4u  /* BVH: cull subtrees against best_t*(1+margin) instead of the reference's un-narrowed range.
-                                    Same closest hit unless float rounding exceeds the margin; off = reference-exact traversal. */
+#define RTNW_F_CULL_NARROW   4u  /* reserved (accepted and ignored): the cooperative BVH traversal always tests exactly the nodes
+                                    and leaves the reference's un-narrowed bvh_node::hit tests */
 #define RTNW_F_COUNTERS      8u  /* fill the optional work counters in rtnw_stats */
 
 typedef struct rtnw_render_params {
@@ -167,7 +167,7 @@ typedef struct rtnw_render_params {
     float t_max;            /* MAXFLOAT */
     uint32_t background;    /* rtnw_background */
     uint32_t flags;         /* RTNW_F_* */
-    uint64_t seed;          /* Philox key; the sample stream is a function of (seed, pixel, sample) only */
+    uint64_t seed;          /* Philox key; the sample stream of a path is a function of (seed, pixel, sample) only */
 } rtnw_render_params;
 
 typedef struct rtnw_stats {
@@ -211,6 +211,10 @@ int rtnw_ctx_destroy(rtnw_ctx* ctx);
 /* copy the device properties the roofline needs: sm_count, clock kHz, smem per block optin, l2 bytes */
 int rtnw_ctx_info(rtnw_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t* smem_optin, int32_t* l2_bytes);
 
+/* measured FP32 peak of the device in TFLOP/s (independent FFMA chains, FMA = 2 flops): the denominator of the
+ * FP32-issue roofline the path is reported against (not part of the reference) */
+int rtnw_measure_fp32_peak(rtnw_ctx* ctx, float* tflops);
+
 int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out);
 int rtnw_scene_free(rtnw_ctx* ctx, rtnw_scene* scene);
 
@@ -226,8 +230,8 @@ int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera
                        const rtnw_render_params* params, float* accum_rgb_dev, void* cuda_stream, rtnw_stats* stats);
 
 /* Deterministic closest-hit query: one `world->hit(r, t_min, t_max, rec)` per ray (PSC/main.cpp:27).  Host buffers.
- * flags: RTNW_F_CULL_NARROW selects the narrowed traversal; media draw their free-flight number from
- * Philox(seed, ray.key, medium leaf id), so results do not depend on traversal order. */
+ * flags: reserved.  Media draw their free-flight number from Philox(seed; medium leaf id, depth 0, sample 0, pixel = ray.key),
+ * so results do not depend on traversal order. */
 int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, size_t n, float t_min, float t_max,
                uint32_t flags, uint64_t seed, rtnw_hit* out);
 
@@ -237,7 +241,7 @@ int rtnw_eval_texture(rtnw_ctx* ctx, const rtnw_scene* scene, int32_t tex_id, co
 int rtnw_eval_perlin(rtnw_ctx* ctx, const rtnw_scene* scene, int32_t which, const float* xyz, size_t n, float* out);
 
 /* material::emitted + material::scatter for n (ray, hit) pairs; hit[i].mat_id selects the material.
- * Random draws come from the sequential Philox stream (seed, pixel=i, sample=0) starting at draw 0.
+ * Random draws come from the path stream (seed, pixel=i, sample=0) starting at its first draw.
  * out_scattered[i] = scattered ray; out_atten = n x 3; out_emitted = n x 3; out_flag[i] = scatter's return value. */
 int rtnw_scatter(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays_in, const rtnw_hit* hits, size_t n,
                  uint64_t seed, rtnw_ray* out_scattered, float* out_atten, float* out_emitted, int32_t* out_flag);

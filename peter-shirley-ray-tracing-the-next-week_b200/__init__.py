@@ -110,7 +110,7 @@ assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 48
 
 # every symbol include/rtnw.h and include/rtnw_host.h declare (tests check the libraries export all of them)
 DEVICE_SYMBOLS = ["rtnw_last_error", "rtnw_abi_version", "rtnw_device_count", "rtnw_ctx_create", "rtnw_ctx_destroy",
-                  "rtnw_ctx_info", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
+                  "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
                   "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays"]
 HOST_SYMBOLS = ["rtnw_host_last_error", "rtnw_host_scene_build", "rtnw_host_scene_free", "rtnw_host_scene_desc",
                 "rtnw_host_scene_leaf_count", "rtnw_host_scene_camera", "rtnw_host_scene_view", "rtnw_host_make_camera",
@@ -164,6 +164,7 @@ def device_lib() -> C.CDLL:
         L.rtnw_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.rtnw_ctx_destroy.argtypes = [C.c_void_p]
         L.rtnw_ctx_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+        L.rtnw_measure_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.rtnw_scene_upload.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
         L.rtnw_scene_free.argtypes = [C.c_void_p, C.c_void_p]
         L.rtnw_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]
@@ -267,6 +268,11 @@ class Context:
         v = [C.c_int32() for _ in range(4)]
         _check_dev(device_lib().rtnw_ctx_info(self._h, *[C.byref(x) for x in v]))
         return dict(sm_count=v[0].value, clock_khz=v[1].value, smem_optin=v[2].value, l2_bytes=v[3].value)
+
+    def fp32_peak_tflops(self) -> float:
+        v = C.c_float()
+        _check_dev(device_lib().rtnw_measure_fp32_peak(self._h, C.byref(v)))
+        return float(v.value)
 
     def upload(self, desc) -> "DeviceScene":
         return DeviceScene(self, desc)

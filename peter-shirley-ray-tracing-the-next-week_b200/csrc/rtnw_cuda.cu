@@ -196,6 +196,17 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     out[q] = o;
 }
 
+// FP32 issue peak of the device, measured: 8 independent FFMA chains per thread (the roofline denominator of bench.py)
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+        a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;  // keeps the chains alive
+}
+
 __global__ void k_eval_texture(const scene_view S, int tex, const float* __restrict__ uvp, size_t n, float* __restrict__ rgb) {
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -621,6 +632,28 @@ int rtnw_ctx_info(rtnw_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t*
     if (clock_khz) *clock_khz = ctx->clock_khz;
     if (smem_optin) *smem_optin = ctx->smem_optin;
     if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+    return RTNW_OK;
+}
+
+int rtnw_measure_fp32_peak(rtnw_ctx* ctx, float* tflops) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!tflops) return fail(RTNW_ERR_INVALID, "null argument");
+    dev_buf d;
+    CUDA_TRY(d.alloc(sizeof(float)));
+    const int iters = 1 << 14, blocks = ctx->sm_count * 32;
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms the clocks up
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_fma_peak<<<blocks, 256, 0, ctx->stream>>>(d.as<float>(), iters);
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const float tf = 2.0f * 8.0f * (float)iters * 256.0f * (float)blocks / (ms * 1e-3f) / 1e12f;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
     return RTNW_OK;
 }
 

@@ -16,6 +16,8 @@ struct device_bridge {
 };
 void set_device_bridge(const device_bridge& b);
 const device_bridge& get_device_bridge();
+// defined in cuda_bridge.cpp (programs that link librtnw.so): serve the four virtuals from GPU `device`
+int install_cuda_bridge(int device, unsigned long long seed = 1);
 }  // namespace rtnw
 
 #endif
