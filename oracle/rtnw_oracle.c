@@ -591,6 +591,24 @@ int rtnw_oracle_trace(const rtnw_scene_desc* d, const rtnw_ray* rays, size_t n, 
     return RTNW_OK;
 }
 
+/* per-ray work counters of the reference traversal (design aid): counts[2*i] = aabb tests, counts[2*i+1] = primitive tests */
+int rtnw_oracle_trace_counts(const rtnw_scene_desc* d, const rtnw_ray* rays, size_t n, float t_min, float t_max, uint64_t seed,
+                             uint32_t* counts) {
+    stream g;
+    stream_init(&g, seed);
+    ctx c = {d, &g};
+    for (size_t i = 0; i < n; ++i) {
+        begin_path(&g, rays[i].key, 0);
+        const ray r = to_ray(&rays[i]);
+        hit_record rec;
+        const uint64_t b0 = g.box_tests, p0 = g.prim_tests;
+        world_hit(&c, &r, t_min, t_max, &rec);
+        counts[2 * i] = (uint32_t)(g.box_tests - b0);
+        counts[2 * i + 1] = (uint32_t)(g.prim_tests - p0);
+    }
+    return RTNW_OK;
+}
+
 /* the sample loop, PSC/main.cpp:299-313; accum = per-pixel sums; stats = {paths, rays, box tests, prim tests, seconds} */
 int rtnw_oracle_render(const rtnw_scene_desc* d, const rtnw_camera* cam, const rtnw_render_params* P, float* accum, double* stats) {
     stream g;

@@ -17,10 +17,10 @@
 using namespace rtnw_dev;
 
 #ifndef RTNW_BLOCK
-#define RTNW_BLOCK 128
+#define RTNW_BLOCK 256
 #endif
 #ifndef RTNW_MIN_BLOCKS
-#define RTNW_MIN_BLOCKS 3   // resident blocks per SM the register allocation is sized for
+#define RTNW_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for
 #endif
 
 // ================================================================================================ kernels

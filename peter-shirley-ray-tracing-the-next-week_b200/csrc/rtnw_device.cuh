@@ -262,7 +262,7 @@ __device__ __forceinline__ bool hit_boundary(const scene_view& S, int first, int
 struct medium_key { uint32_t k0, k1, pixel, sample, depth; };
 
 // PSC/constant_medium.h:26-50
-__device__ __noinline__ bool hit_medium(const scene_view& S, int i, float4 A, uint32_t tag, const ray_t& r_frame, float a_frame,
+__device__ __forceinline__ bool hit_medium(const scene_view& S, int i, float4 A, uint32_t tag, const ray_t& r_frame, float a_frame,
                                            float t_lo, float t_hi, const medium_key& mk, float& t) {
     ray_t r = r_frame;
     float a = a_frame;
@@ -395,13 +395,15 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
 //     children one level deeper, so it never holds more than BLOCK*(depth+1) tasks (depth is validated at upload),
 //     and every round but the last few runs with all threads busy.
 #ifndef RTNW_QN
-#define RTNW_QN 3072  // node task stack: room for trees of depth <= RTNW_QN/BLOCK - 1
+#define RTNW_QN 6144  // node task stack: room for trees of depth <= RTNW_QN/BLOCK - 1
 #endif
 #ifndef RTNW_QL
-#define RTNW_QL 2048  // leaf queue; flushed whenever fewer than 2*BLOCK slots are free
+#define RTNW_QL 4096  // leaf queue; flushed whenever fewer than 2*BLOCK slots are free
 #endif
 template <int BLOCK>
 struct coop_smem {
+    static_assert(BLOCK <= 256 && BLOCK % 32 == 0, "a task carries its owner slot in 8 bits");
+    static_assert(RTNW_QL >= 4 * BLOCK && RTNW_QN >= 4 * BLOCK, "queues too small for the block");
     float4 ray_o[BLOCK];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
     float4 ray_d[BLOCK];  // d.xyz, w = dot(d,d)
     float4 ray_i[BLOCK];  // 1/d, w = time
@@ -491,32 +493,34 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         if (tid < take) task = sm.q[base + tid];
         if (tid == 0) *n_nxt = base;  // pop; this round's pushes land on top of what remains
         __syncthreads();
-        bool pn0 = false, pn1 = false, pl0 = false, pl1 = false;
-        int left = 0, right = 0;
-        const int slot = (int)(task >> 24);
-        if (tid < take) {
-            const int node = (int)(task & 0xffffffu);
-            const float4 n0 = __ldg(&S.nodes[4 * node]), n1 = __ldg(&S.nodes[4 * node + 1]);
-            const float4 n2 = __ldg(&S.nodes[4 * node + 2]), n3 = __ldg(&S.nodes[4 * node + 3]);
-            const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
-            const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
-            left = __float_as_int(n0.w); right = __float_as_int(n1.w);
-            if (left >= 0) {
-                if (COUNT) cnt.box_tests++;
-                pn0 = hit_aabb(make_float4(n0.x, n0.y, n0.z, n1.x), make_float4(n1.y, n1.z, 0.f, 0.f), o, inv, t_min, ro.w);
-            } else {
-                pl0 = true;  // leaves are handed the ray without a box test (PSC/bvh.h:34)
+        if ((tid & ~31) < take) {  // warps without a task this round go straight to the barrier
+            bool pn0 = false, pn1 = false, pl0 = false, pl1 = false;
+            int left = 0, right = 0;
+            const int slot = (int)(task >> 24);
+            if (tid < take) {
+                const int node = (int)(task & 0xffffffu);
+                const float4 n0 = __ldg(&S.nodes[4 * node]), n1 = __ldg(&S.nodes[4 * node + 1]);
+                const float4 n2 = __ldg(&S.nodes[4 * node + 2]), n3 = __ldg(&S.nodes[4 * node + 3]);
+                const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
+                const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
+                left = __float_as_int(n0.w); right = __float_as_int(n1.w);
+                if (left >= 0) {
+                    if (COUNT) cnt.box_tests++;
+                    pn0 = hit_aabb(make_float4(n0.x, n0.y, n0.z, n1.x), make_float4(n1.y, n1.z, 0.f, 0.f), o, inv, t_min, ro.w);
+                } else {
+                    pl0 = true;  // leaves are handed the ray without a box test (PSC/bvh.h:34)
+                }
+                if (right >= 0) {
+                    if (COUNT) cnt.box_tests++;
+                    pn1 = hit_aabb(make_float4(n2.x, n2.y, n2.z, n3.x), make_float4(n3.y, n3.z, 0.f, 0.f), o, inv, t_min, ro.w);
+                } else {
+                    pl1 = right != RTNW_REF_NONE;
+                }
             }
-            if (right >= 0) {
-                if (COUNT) cnt.box_tests++;
-                pn1 = hit_aabb(make_float4(n2.x, n2.y, n2.z, n3.x), make_float4(n3.y, n3.z, 0.f, 0.f), o, inv, t_min, ro.w);
-            } else {
-                pl1 = right != RTNW_REF_NONE;
-            }
+            const bool ok_n = queue_push2(sm.q, n_nxt, RTNW_QN, pn0, RTNW_TASK(slot, left), pn1, RTNW_TASK(slot, right));
+            const bool ok_l = queue_push2(sm.ql, &sm.nl, RTNW_QL, pl0, RTNW_TASK(slot, ~left), pl1, RTNW_TASK(slot, ~right));
+            if (!(ok_n && ok_l)) sm.overflow = 1;
         }
-        const bool ok_n = queue_push2(sm.q, n_nxt, RTNW_QN, pn0, RTNW_TASK(slot, left), pn1, RTNW_TASK(slot, right));
-        const bool ok_l = queue_push2(sm.ql, &sm.nl, RTNW_QL, pl0, RTNW_TASK(slot, ~left), pl1, RTNW_TASK(slot, ~right));
-        if (!(ok_n && ok_l)) sm.overflow = 1;
         __syncthreads();
         if (sm.nl > RTNW_QL - 2 * BLOCK) coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
     }
