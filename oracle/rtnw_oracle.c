@@ -53,6 +53,7 @@ typedef struct {
     uint64_t x;
     int seeded;
     int depth;          /* index of the current top-level closest-hit query of the path */
+    int in_boundary;    /* > 0 while a constant_medium probes its boundary (those hit() calls are not counted as tests) */
     uint64_t rays, box_tests, prim_tests;
 } stream;
 
@@ -219,7 +220,7 @@ static int prim_hit(const ctx* c, int s, const ray* r_outer, float t_min, float 
     int h = 0;
     *used = 1;
     rec->face = 0;
-    c->g->prim_tests++;
+    if (!c->g->in_boundary) c->g->prim_tests++;
     switch (kind) {
         case RTNW_PRIM_SPHERE: h = sphere_hit(V(p->f[0], p->f[1], p->f[2]), p->f[3], 1, &r, t_min, t_max, rec); break;
         case RTNW_PRIM_MOVING_SPHERE: { /* PSC/sphere.h:81-83 */
@@ -238,8 +239,12 @@ static int prim_hit(const ctx* c, int s, const ray* r_outer, float t_min, float 
             int bfirst, bcount, leaf;
             memcpy(&bfirst, &p->f[1], 4); memcpy(&bcount, &p->f[2], 4); memcpy(&leaf, &p->f[3], 4);
             hit_record rec1, rec2;
-            if (slots_hit(c, bfirst, bcount, &r, -FLT_MAX, FLT_MAX, &rec1)) {
-                if (slots_hit(c, bfirst, bcount, &r, rec1.t + 0.0001, FLT_MAX, &rec2)) {
+            c->g->in_boundary++;
+            const int h1 = slots_hit(c, bfirst, bcount, &r, -FLT_MAX, FLT_MAX, &rec1);
+            const int h2 = h1 && slots_hit(c, bfirst, bcount, &r, rec1.t + 0.0001, FLT_MAX, &rec2);
+            c->g->in_boundary--;
+            if (h1) {
+                if (h2) {
                     if (rec1.t < t_min) rec1.t = t_min;
                     if (rec2.t > t_max) rec2.t = t_max;
                     if (rec1.t >= rec2.t) break;

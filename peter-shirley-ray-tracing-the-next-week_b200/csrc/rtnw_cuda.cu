@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -410,36 +411,147 @@ struct stream_builder {
         return true;
     }
 
-    std::vector<float4> nodes2;        // 4 float4 per bvh_node, children rewritten (see scene_view::nodes)
+    // ---- gate tree (rtnw_device.cuh, "block-cooperative closest hit") ------------------------------------------
+    struct gate_t { float bmin[3], bmax[3]; int32_t leaf0, leaf1; };
+    struct bin_node { float bmin[3], bmax[3]; int left, right, gate; };  // binary SAH tree over gates; gate >= 0: leaf
+    std::vector<gate_t> gates;          // all items
+    std::vector<int2> gate_leaves;      // device table
+    std::vector<float4> wnodes;         // device table, 8 float4 per wide node
     std::vector<uint8_t> node_seen;
+    int max_wide_depth = 0;
 
-    // bvh_node `idx`: leaves are appended to the record stream in left-to-right order (the key's tie rule relies on
-    // it), the node itself goes to the two-box table with its leaf children rewritten to record indices.
-    bool emit_node(int32_t idx, int depth) {
+    // bvh_node `idx` with own box [bmin,bmax]: its leaves go to the record stream in left-to-right order (the key's tie
+    // rule relies on it); every leaf child becomes (part of) a gate guarded by THIS node's box.
+    bool collect_gates(int32_t idx, const float* bmin, const float* bmax, int depth, std::vector<int>& mine) {
         if (idx < 0 || idx >= d.n_nodes) return bad("BVH node index out of range");
-        if (depth >= RTNW_QN / RTNW_BLOCK - 1) return bad("BVH deeper than the cooperative task stack allows (RTNW_QN / RTNW_BLOCK - 1 levels)");
+        if (depth > 4096) return bad("BVH deeper than 4096 levels (cycle?)");
         if (node_seen[idx]) return bad("BVH node referenced twice");
         node_seen[idx] = 1;
         const rtnw_bvh_node& n = d.nodes[idx];
         if (n.left == RTNW_REF_NONE) return bad("BVH node without a left child");
-        int32_t child[2] = {n.left, n.right};
+        const int32_t child[2] = {n.left, n.right};
         const int32_t cnt[2] = {n.lcount, n.rcount};
+        const float* cmin[2] = {n.lmin, n.rmin};
+        const float* cmax[2] = {n.lmax, n.rmax};
+        gate_t g;
+        for (int a = 0; a < 3; ++a) { g.bmin[a] = bmin[a]; g.bmax[a] = bmax[a]; }
+        g.leaf0 = g.leaf1 = -1;
         for (int w = 0; w < 2; ++w) {
             if (child[w] == RTNW_REF_NONE) continue;
             if (child[w] >= 0) {
-                if (!emit_node(child[w], depth + 1)) return false;
+                if (!collect_gates(child[w], cmin[w], cmax[w], depth + 1, mine)) return false;
             } else {
                 const size_t first = recs.size();
                 if (!emit_prims(~child[w], cnt[w], false, false)) return false;
                 if (recs.size() == first) return bad("empty BVH leaf");
-                child[w] = ~(int32_t)first;
+                (g.leaf0 < 0 ? g.leaf0 : g.leaf1) = (int32_t)first;
             }
         }
-        if (recs.size() >= (1u << 24)) return bad("scene exceeds 2^24 records");
-        nodes2[4 * (size_t)idx + 0] = make_float4(n.lmin[0], n.lmin[1], n.lmin[2], bits(child[0]));
-        nodes2[4 * (size_t)idx + 1] = make_float4(n.lmax[0], n.lmax[1], n.lmax[2], bits(child[1]));
-        nodes2[4 * (size_t)idx + 2] = make_float4(n.rmin[0], n.rmin[1], n.rmin[2], 0.f);
-        nodes2[4 * (size_t)idx + 3] = make_float4(n.rmax[0], n.rmax[1], n.rmax[2], 0.f);
+        if (g.leaf0 >= 0) {
+            mine.push_back((int)gates.size());
+            gates.push_back(g);
+            gate_leaves.push_back(make_int2(g.leaf0, g.leaf1));
+        }
+        return true;
+    }
+
+    static double half_area(const float* lo, const float* hi) {
+        const double x = (double)hi[0] - lo[0], y = (double)hi[1] - lo[1], z = (double)hi[2] - lo[2];
+        return x * y + y * z + z * x;
+    }
+    void bounds_of(const std::vector<int>& ids, size_t lo, size_t hi, float* bmin, float* bmax) const {
+        for (int a = 0; a < 3; ++a) { bmin[a] = gates[ids[lo]].bmin[a]; bmax[a] = gates[ids[lo]].bmax[a]; }
+        for (size_t q = lo + 1; q < hi; ++q)
+            for (int a = 0; a < 3; ++a) {  // exact unions: the monotonicity argument needs nothing else
+                bmin[a] = std::fmin(bmin[a], gates[ids[q]].bmin[a]);
+                bmax[a] = std::fmax(bmax[a], gates[ids[q]].bmax[a]);
+            }
+    }
+    // binary SAH split by full sweep over the three centroid orders (gate counts are small: <= #leaves)
+    int build_binary(std::vector<int>& ids, size_t lo, size_t hi, std::vector<bin_node>& out) {
+        const int me = (int)out.size();
+        out.push_back(bin_node());
+        bin_node nd;
+        bounds_of(ids, lo, hi, nd.bmin, nd.bmax);
+        nd.left = nd.right = -1;
+        nd.gate = -1;
+        if (hi - lo == 1) {
+            nd.gate = ids[lo];
+            out[me] = nd;
+            return me;
+        }
+        double best_cost = 1e300;
+        int best_axis = 0;
+        size_t best_split = lo + (hi - lo) / 2;
+        std::vector<double> right_area(hi - lo);
+        for (int axis = 0; axis < 3; ++axis) {
+            std::stable_sort(ids.begin() + lo, ids.begin() + hi, [&](int x, int y) {
+                return gates[x].bmin[axis] + gates[x].bmax[axis] < gates[y].bmin[axis] + gates[y].bmax[axis];
+            });
+            float rmin[3], rmax[3];
+            for (size_t q = hi; q-- > lo;) {
+                if (q == hi - 1) { for (int a = 0; a < 3; ++a) { rmin[a] = gates[ids[q]].bmin[a]; rmax[a] = gates[ids[q]].bmax[a]; } }
+                else for (int a = 0; a < 3; ++a) { rmin[a] = std::fmin(rmin[a], gates[ids[q]].bmin[a]); rmax[a] = std::fmax(rmax[a], gates[ids[q]].bmax[a]); }
+                right_area[q - lo] = half_area(rmin, rmax);
+            }
+            float lmin[3], lmax[3];
+            for (size_t q = lo; q + 1 < hi; ++q) {
+                if (q == lo) { for (int a = 0; a < 3; ++a) { lmin[a] = gates[ids[q]].bmin[a]; lmax[a] = gates[ids[q]].bmax[a]; } }
+                else for (int a = 0; a < 3; ++a) { lmin[a] = std::fmin(lmin[a], gates[ids[q]].bmin[a]); lmax[a] = std::fmax(lmax[a], gates[ids[q]].bmax[a]); }
+                const double cost = half_area(lmin, lmax) * (double)(q - lo + 1) + right_area[q + 1 - lo] * (double)(hi - q - 1);
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = q + 1; }
+            }
+        }
+        std::stable_sort(ids.begin() + lo, ids.begin() + hi, [&](int x, int y) {
+            return gates[x].bmin[best_axis] + gates[x].bmax[best_axis] < gates[y].bmin[best_axis] + gates[y].bmax[best_axis];
+        });
+        nd.left = build_binary(ids, lo, best_split, out);
+        nd.right = build_binary(ids, best_split, hi, out);
+        out[me] = nd;
+        return me;
+    }
+    // collapse the binary tree into 4-wide nodes: repeatedly open the child with the largest box
+    int emit_wide(const std::vector<bin_node>& bt, int root, int depth) {
+        if (depth > max_wide_depth) max_wide_depth = depth;
+        int kids[4], nk = 0;
+        if (bt[root].gate >= 0) kids[nk++] = root;
+        else { kids[nk++] = bt[root].left; kids[nk++] = bt[root].right; }
+        while (nk < 4) {
+            int pick = -1;
+            double area = -1;
+            for (int q = 0; q < nk; ++q)
+                if (bt[kids[q]].gate < 0 && half_area(bt[kids[q]].bmin, bt[kids[q]].bmax) > area) { area = half_area(bt[kids[q]].bmin, bt[kids[q]].bmax); pick = q; }
+            if (pick < 0) break;
+            const int open = kids[pick];
+            kids[pick] = bt[open].left;
+            kids[nk++] = bt[open].right;
+        }
+        const size_t me = wnodes.size() / 8;
+        wnodes.resize(wnodes.size() + 8, make_float4(0, 0, 0, 0));
+        float v[6][4];
+        int32_t ref[4];
+        for (int q = 0; q < 4; ++q) {
+            ref[q] = RTNW_REF_NONE;
+            for (int a = 0; a < 6; ++a) v[a][q] = 0.f;
+        }
+        for (int q = 0; q < nk; ++q) {
+            const bin_node& c = bt[kids[q]];
+            for (int a = 0; a < 3; ++a) { v[a][q] = c.bmin[a]; v[3 + a][q] = c.bmax[a]; }
+            ref[q] = c.gate >= 0 ? ~c.gate : emit_wide(bt, kids[q], depth + 1);
+        }
+        for (int a = 0; a < 6; ++a) wnodes[8 * me + a] = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
+        wnodes[8 * me + 6] = make_float4(bits(ref[0]), bits(ref[1]), bits(ref[2]), bits(ref[3]));
+        return (int)me;
+    }
+    // one BVH item: returns the root wide node
+    bool emit_bvh_item(const rtnw_item& it, int& root_out) {
+        std::vector<int> mine;
+        if (!collect_gates(it.first, it.bmin, it.bmax, 0, mine)) return false;
+        if (mine.empty()) return bad("BVH without leaves");
+        std::vector<bin_node> bt;
+        bt.reserve(2 * mine.size());
+        const int broot = build_binary(mine, 0, mine.size(), bt);
+        root_out = emit_wide(bt, broot, 0);
         return true;
     }
 
@@ -447,7 +559,6 @@ struct stream_builder {
         if (d.abi_version != RTNW_ABI_VERSION) return bad("scene_desc.abi_version does not match this library");
         if (d.n_items <= 0 || !d.items) return bad("scene has no items");
         if (d.n_nodes >= (1 << 24)) return bad("scene exceeds 2^24 BVH nodes");
-        nodes2.assign(4 * (size_t)std::max(d.n_nodes, 1), make_float4(0, 0, 0, 0));
         node_seen.assign((size_t)std::max(d.n_nodes, 1), 0);
         if (d.n_prim_slots < 0 || d.n_nodes < 0 || d.n_materials < 0 || d.n_textures < 0 || d.n_xform_ops < 1)
             return bad("negative table size (or missing identity transform op 0)");
@@ -484,10 +595,9 @@ struct stream_builder {
             if (it.kind == RTNW_ITEM_PRIMS) {
                 if (!emit_prims(it.first, it.count, true, false)) return false;
             } else if (it.kind == RTNW_ITEM_BVH) {
-                // second record of the item: the root bvh_node's own box; then the leaves of the tree
-                recs[at].a.y = bits(it.first);
-                push(make_float4(it.bmin[0], it.bmin[1], it.bmin[2], it.bmax[0]), it.bmax[1], it.bmax[2], RTNW_TAG(K_EXT, 0, 1, 0), 0, -1);
-                if (!emit_node(it.first, 0)) return false;
+                int wroot = 0;
+                if (!emit_bvh_item(it, wroot)) return false;  // leaves -> record stream, gates + gate tree -> side tables
+                recs[at].a.y = bits(wroot);
             } else {
                 return bad("unknown item kind");
             }
@@ -495,7 +605,10 @@ struct stream_builder {
         }
         cur_item_xf = 0;
         push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_END, 0, 0, 0), 0, -1);
-        if (recs.size() >= (1u << 24)) return bad("scene exceeds 2^24 records");
+        if (recs.size() >= (1u << 24) || gates.size() >= (1u << 24) || wnodes.size() / 8 >= (1u << 24)) return bad("scene exceeds 2^24 records");
+        if (3 * (max_wide_depth + 1) + 1 > RTNW_QN / RTNW_BLOCK) return bad("gate tree deeper than the cooperative task stack allows");
+        if (gate_leaves.empty()) gate_leaves.push_back(make_int2(-1, -1));
+        if (wnodes.empty()) wnodes.resize(8, make_float4(0, 0, 0, 0));
         return true;
     }
 };
@@ -685,8 +798,9 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     const size_t o_recs = off; off += align256(sz_recs);
     const size_t o_leaf = off; off += align256(sz_leaf);
     const size_t o_rxf = off; off += align256(sz_leaf);
-    const size_t sz_nodes = sb.nodes2.size() * sizeof(float4);
+    const size_t sz_nodes = sb.wnodes.size() * sizeof(float4), sz_gates = sb.gate_leaves.size() * sizeof(int2);
     const size_t o_nodes = off; off += align256(sz_nodes);
+    const size_t o_gates = off; off += align256(sz_gates);
     const size_t o_xf = off; off += align256(sz_xf);
     const size_t o_mat = off; off += align256(sz_mat);
     const size_t o_tex = off; off += align256(sz_tex);
@@ -697,7 +811,8 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     std::memcpy(host.data() + o_recs, sb.recs.data(), sz_recs);
     std::memcpy(host.data() + o_leaf, sb.leaf.data(), sz_leaf);
     std::memcpy(host.data() + o_rxf, sb.rec_xf.data(), sz_leaf);
-    std::memcpy(host.data() + o_nodes, sb.nodes2.data(), sz_nodes);
+    std::memcpy(host.data() + o_nodes, sb.wnodes.data(), sz_nodes);
+    std::memcpy(host.data() + o_gates, sb.gate_leaves.data(), sz_gates);
     std::memcpy(host.data() + o_xf, desc->xforms, sz_xf);
     if (sz_mat) std::memcpy(host.data() + o_mat, desc->materials, sz_mat);
     if (sz_tex) std::memcpy(host.data() + o_tex, desc->textures, sz_tex);
@@ -718,7 +833,8 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     s->view.recs = reinterpret_cast<const rec*>(base + o_recs);
     s->view.rec_leaf = reinterpret_cast<const int32_t*>(base + o_leaf);
     s->view.rec_xf = reinterpret_cast<const uint32_t*>(base + o_rxf);
-    s->view.nodes = reinterpret_cast<const float4*>(base + o_nodes);
+    s->view.wnodes = reinterpret_cast<const float4*>(base + o_nodes);
+    s->view.gates = reinterpret_cast<const int2*>(base + o_gates);
     s->view.xforms = reinterpret_cast<const rtnw_xform_op*>(base + o_xf);
     s->view.materials = reinterpret_cast<const rtnw_material*>(base + o_mat);
     s->view.textures = reinterpret_cast<const rtnw_texture*>(base + o_tex);

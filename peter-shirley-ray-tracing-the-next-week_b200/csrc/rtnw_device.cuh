@@ -54,8 +54,9 @@ struct scene_view {
     const float4* ranvec;       // 256 gradients, PSC/perlin.h:82-87
     const uint8_t* perm;        // perm_x | perm_y | perm_z, 256 bytes each, PSC/perlin.h:99-106
     const uint32_t* rec_xf;     // per record: transform chain of the item it belongs to
-    const float4* nodes;        // 4 float4 per bvh_node: {lmin, left} {lmax, right} {rmin, -} {rmax, -}; child >= 0: node
-                                // index, child < 0: ~(first record of the leaf), RTNW_REF_NONE: absent
+    const float4* wnodes;       // gate tree, 8 float4 per 4-wide node: minx[4] miny[4] minz[4] maxx[4] maxy[4] maxz[4], then
+                                // child refs (int4): >= 0 wide node, < 0 ~gate, RTNW_REF_NONE absent; last float4 unused
+    const int2* gates;          // per gate: first records of the (one or two) leaves it guards, -1 = none
     int32_t n_recs, n_materials, n_textures;
 };
 
@@ -346,6 +347,11 @@ __device__ __forceinline__ bool hit_aabb(float4 A, float4 B, f3 o, f3 inv, float
     return !(hi_t <= lo_t);
 }
 
+__device__ __forceinline__ bool hit_aabb6(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, f3 o, f3 inv, float t_lo,
+                                          float t_hi) {
+    return hit_aabb(make_float4(mnx, mny, mnz, mxx), make_float4(mxy, mxz, 0.f, 0.f), o, inv, t_lo, t_hi);
+}
+
 // One primitive record (surface or medium) of a scope whose narrowing limit is `lim`; returns records consumed.
 template <bool COUNT>
 __device__ __forceinline__ int test_record(const scene_view& S, int i, float4 A, float4 B, const ray_t& r, float a, float t_min,
@@ -385,25 +391,34 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
 // ---- block-cooperative closest hit --------------------------------------------------------------------------
 // Every thread of the block owns one ray (or none).  All rays walk the same record stream, item by item:
 //   * a list item (PSC/hitable_list.h:20-32) is scanned by each owner in lockstep: same records, same code, all lanes;
-//   * a BVH item is traversed by the WHOLE BLOCK through a shared-memory task stack.  Because bvh_node::hit gives both
-//     children the un-narrowed range (PSC/bvh.h:34-35) the set of nodes/leaves a ray tests is order independent, so
-//     the work is cut into uniform tasks that any thread can take: a node task (ray, bvh_node whose own box passed)
-//     tests the boxes of the node's two children (64-byte record, the layout of rtnw_bvh_node) and pushes the children
-//     that passed; leaf children go to the leaf queue untested, as in the reference; every (ray, leaf) pair is one
-//     leaf task.  Candidates are merged per ray with atomicMin on the 64-bit key.
-//     The stack is served LIFO, BLOCK tasks at a time: each round pops at most BLOCK tasks and pushes at most 2*BLOCK
-//     children one level deeper, so it never holds more than BLOCK*(depth+1) tasks (depth is validated at upload),
-//     and every round but the last few runs with all threads busy.
+//   * a BVH item is traversed by the WHOLE BLOCK through a shared-memory task stack.
+//
+// Which leaves does the reference test?  bvh_node::hit hands both children the un-narrowed range (PSC/bvh.h:34-35), so
+// a leaf is tested iff the own box of every bvh_node above it passes aabb::hit(r, tmin, tmax0).  A bvh_node's box is
+// surrounding_box(left, right) (PSC/bvh.h:120, PSC/aabb.h:54-62), an exact fmin/fmax union, and every operation of the
+// slab test (subtract, multiply by 1/d, swap, the NaN-ignoring min/max selects) is monotonic under IEEE rounding:
+// a larger box yields a superset interval IN FLOATING POINT.  Hence "box of the leaf's parent passes" already implies
+// that all ancestors pass, and the reference's leaf set is exactly { leaves whose parent ("gate") box passes }
+// (checked numerically on all node pairs of the test scenes).  The hierarchy above the gates is only an
+// index, so the upload builds its own: a 4-wide SAH tree over the gate boxes whose interior boxes are again exact unions
+// (so, by the same monotonicity, they can never cull a passing gate), tested with the same aabb::hit arithmetic.
+// Results are identical to the reference's tree; the number of box tests, tasks and rounds is a fraction of it.
+//
+// Tasks are uniform and any thread can take any of them: a node task (ray, wide node) tests the node's <= 4 child
+// boxes and pushes the children that passed — wide nodes back on the stack, gates to the leaf queue; a gate task runs
+// leaf->hit(r, tmin, tmax0) for the gate's one or two leaves.  Candidates are merged per ray with atomicMin on the
+// 64-bit key.  The stack is served LIFO, BLOCK tasks at a time: a round pops <= BLOCK tasks and pushes <= 4*BLOCK
+// children one level deeper, so it never holds more than BLOCK*(3*depth+1) tasks (validated at upload).
 #ifndef RTNW_QN
-#define RTNW_QN 6144  // node task stack: room for trees of depth <= RTNW_QN/BLOCK - 1
+#define RTNW_QN 6144  // node task stack
 #endif
 #ifndef RTNW_QL
-#define RTNW_QL 4096  // leaf queue; flushed whenever fewer than 2*BLOCK slots are free
+#define RTNW_QL 6144  // gate queue; flushed whenever fewer than 4*BLOCK slots are free
 #endif
 template <int BLOCK>
 struct coop_smem {
     static_assert(BLOCK <= 256 && BLOCK % 32 == 0, "a task carries its owner slot in 8 bits");
-    static_assert(RTNW_QL >= 4 * BLOCK && RTNW_QN >= 4 * BLOCK, "queues too small for the block");
+    static_assert(RTNW_QL >= 8 * BLOCK && RTNW_QN >= 8 * BLOCK, "queues too small for the block");
     float4 ray_o[BLOCK];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
     float4 ray_d[BLOCK];  // d.xyz, w = dot(d,d)
     float4 ray_i[BLOCK];  // 1/d, w = time
@@ -415,33 +430,10 @@ struct coop_smem {
     int nl;
     int overflow;         // a push did not fit (cannot happen for validated scenes); reported to the host
 };
-// task = owner slot (8 bits) | node index or leaf record (24 bits)
+// task = owner slot (8 bits) | wide node index or gate index (24 bits)
 #define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 24) | (uint32_t)(idx))
 
-// warp-aggregated append of up to two entries per lane; returns false if an entry did not fit
-__device__ __forceinline__ bool queue_push2(uint32_t* q, int* count, int cap, bool p0, uint32_t v0, bool p1, uint32_t v1) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned b0 = __ballot_sync(FULL, p0), b1 = __ballot_sync(FULL, p1);
-    const int c0 = __popc(b0), total = c0 + __popc(b1);
-    if (total == 0) return true;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(count, total);
-    base = __shfl_sync(FULL, base, 0);
-    const unsigned lt = (1u << lane) - 1u;
-    bool ok = true;
-    if (p0) {
-        const int at = base + __popc(b0 & lt);
-        if (at < cap) q[at] = v0; else ok = false;
-    }
-    if (p1) {
-        const int at = base + c0 + __popc(b1 & lt);
-        if (at < cap) q[at] = v1; else ok = false;
-    }
-    return ok;
-}
-
-// every queued (ray, leaf) pair is one leaf->hit(r, tmin, tmax0); all threads, then the queue is empty again
+// every queued (ray, gate) pair: leaf->hit(r, tmin, tmax0) for the gate's leaves; all threads, then the queue is empty
 template <int BLOCK, bool COUNT>
 __device__ __forceinline__ void coop_flush_leaves(const scene_view& S, coop_smem<BLOCK>& sm, float t_min, uint32_t k0, uint32_t k1,
                                                   trav_counters& cnt) {
@@ -450,12 +442,17 @@ __device__ __forceinline__ void coop_flush_leaves(const scene_view& S, coop_smem
 #pragma unroll 1
     for (int q = tid; q < nl; q += BLOCK) {
         const uint32_t task = sm.ql[q];
-        const int slot = (int)(task >> 24), rec = (int)(task & 0xffffffu);
+        const int slot = (int)(task >> 24);
+        const int2 g = __ldg(&S.gates[task & 0xffffffu]);
         const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
         const uint4 mq = sm.mkey[slot];
         ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
         medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-        const hkey_t k = test_leaf<COUNT>(S, rec, r, rd.w, t_min, ro.w, mk, cnt);
+        hkey_t k = test_leaf<COUNT>(S, g.x, r, rd.w, t_min, ro.w, mk, cnt);
+        if (g.y >= 0) {
+            const hkey_t k2 = test_leaf<COUNT>(S, g.y, r, rd.w, t_min, ro.w, mk, cnt);
+            if (k2 < k) k = k2;
+        }
         if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
     }
     __syncthreads();
@@ -463,26 +460,25 @@ __device__ __forceinline__ void coop_flush_leaves(const scene_view& S, coop_smem
     __syncthreads();
 }
 
-// Closest hit of the block's rays against the BVH item whose root is bvh_node `root` with own box [RA,RB].  Owners
-// have already written their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
+// Closest hit of the block's rays against the BVH item whose gate tree has root `root`.  Owners have already written
+// their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
 template <int BLOCK, bool COUNT>
-__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, float4 RA, float4 RB, bool active,
-                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt) {
+__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, bool active, float t_min,
+                                              uint32_t k0, uint32_t k1, trav_counters& cnt) {
+    constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, lt = (1u << lane) - 1u;
     if (tid < 2) sm.n[tid] = 0;
     if (tid == 2) sm.nl = 0;
     __syncthreads();
-    {   // bvh_node::hit of the root: its own box, tested by the owner (PSC/bvh.h:31)
-        bool pass = false;
-        if (active) {
-            const float4 ro = sm.ray_o[tid], ri = sm.ray_i[tid];
-            if (COUNT) cnt.box_tests++;
-            pass = hit_aabb(RA, RB, mk3(ro.x, ro.y, ro.z), mk3(ri.x, ri.y, ri.z), t_min, ro.w);
-        }
-        queue_push2(sm.q, &sm.n[0], RTNW_QN, pass, RTNW_TASK(tid, root), false, 0u);
+    {   // one task per ray: the root of the gate tree
+        const unsigned b = __ballot_sync(FULL, active);
+        int base = 0;
+        if (lane == 0 && b) base = atomicAdd(&sm.n[0], __popc(b));
+        base = __shfl_sync(FULL, base, 0);
+        if (active) sm.q[base + __popc(b & lt)] = RTNW_TASK(tid, root);
     }
     __syncthreads();
-    // ---- node rounds: a task = one node whose box passed; it tests its children's boxes
 #pragma unroll 1
     for (int round = 0;; ++round) {
         const int n = sm.n[round & 1];
@@ -494,35 +490,56 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         if (tid == 0) *n_nxt = base;  // pop; this round's pushes land on top of what remains
         __syncthreads();
         if ((tid & ~31) < take) {  // warps without a task this round go straight to the barrier
-            bool pn0 = false, pn1 = false, pl0 = false, pl1 = false;
-            int left = 0, right = 0;
             const int slot = (int)(task >> 24);
+            int ref[4] = {RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE};
+            bool pass[4] = {false, false, false, false};
             if (tid < take) {
-                const int node = (int)(task & 0xffffffu);
-                const float4 n0 = __ldg(&S.nodes[4 * node]), n1 = __ldg(&S.nodes[4 * node + 1]);
-                const float4 n2 = __ldg(&S.nodes[4 * node + 2]), n3 = __ldg(&S.nodes[4 * node + 3]);
+                const float4* N = S.wnodes + 8 * (size_t)(task & 0xffffffu);
+                const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
+                const float4 rf = __ldg(N + 6);
                 const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
                 const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
-                left = __float_as_int(n0.w); right = __float_as_int(n1.w);
-                if (left >= 0) {
-                    if (COUNT) cnt.box_tests++;
-                    pn0 = hit_aabb(make_float4(n0.x, n0.y, n0.z, n1.x), make_float4(n1.y, n1.z, 0.f, 0.f), o, inv, t_min, ro.w);
-                } else {
-                    pl0 = true;  // leaves are handed the ray without a box test (PSC/bvh.h:34)
-                }
-                if (right >= 0) {
-                    if (COUNT) cnt.box_tests++;
-                    pn1 = hit_aabb(make_float4(n2.x, n2.y, n2.z, n3.x), make_float4(n3.y, n3.z, 0.f, 0.f), o, inv, t_min, ro.w);
-                } else {
-                    pl1 = right != RTNW_REF_NONE;
-                }
+                ref[0] = __float_as_int(rf.x); ref[1] = __float_as_int(rf.y); ref[2] = __float_as_int(rf.z); ref[3] = __float_as_int(rf.w);
+                pass[0] = ref[0] != RTNW_REF_NONE && hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, ro.w);
+                pass[1] = ref[1] != RTNW_REF_NONE && hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, ro.w);
+                pass[2] = ref[2] != RTNW_REF_NONE && hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, ro.w);
+                pass[3] = ref[3] != RTNW_REF_NONE && hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, ro.w);
+                if (COUNT) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
             }
-            const bool ok_n = queue_push2(sm.q, n_nxt, RTNW_QN, pn0, RTNW_TASK(slot, left), pn1, RTNW_TASK(slot, right));
-            const bool ok_l = queue_push2(sm.ql, &sm.nl, RTNW_QL, pl0, RTNW_TASK(slot, ~left), pl1, RTNW_TASK(slot, ~right));
-            if (!(ok_n && ok_l)) sm.overflow = 1;
+            // warp-aggregated appends: wide nodes back onto the stack, gates to the leaf queue
+            unsigned bn[4], bl[4];
+            int tn = 0, tl = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bn[j] = __ballot_sync(FULL, pass[j] && ref[j] >= 0);
+                bl[j] = __ballot_sync(FULL, pass[j] && ref[j] < 0);
+                tn += __popc(bn[j]); tl += __popc(bl[j]);
+            }
+            int base_n = 0, base_l = 0;
+            if (lane == 0) {
+                if (tn) base_n = atomicAdd(n_nxt, tn);
+                if (tl) base_l = atomicAdd(&sm.nl, tl);
+            }
+            base_n = __shfl_sync(FULL, base_n, 0);
+            base_l = __shfl_sync(FULL, base_l, 0);
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (pass[j]) {
+                    if (ref[j] >= 0) {
+                        const int at = base_n + __popc(bn[j] & lt);
+                        if (at < RTNW_QN) sm.q[at] = RTNW_TASK(slot, ref[j]); else ok = false;
+                    } else {
+                        const int at = base_l + __popc(bl[j] & lt);
+                        if (at < RTNW_QL) sm.ql[at] = RTNW_TASK(slot, ~ref[j]); else ok = false;
+                    }
+                }
+                base_n += __popc(bn[j]); base_l += __popc(bl[j]);
+            }
+            if (!ok) sm.overflow = 1;
         }
         __syncthreads();
-        if (sm.nl > RTNW_QL - 2 * BLOCK) coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
+        if (sm.nl > RTNW_QL - 4 * BLOCK) coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
     }
     coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
 }
@@ -550,8 +567,7 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
             sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
             sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
             sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-            const float4 RA = __ldg(&S.recs[i + 1].a), RB = __ldg(&S.recs[i + 1].b);  // the root bvh_node's own box
-            coop_bvh_item<BLOCK, COUNT>(S, sm, __float_as_int(IA.y), RA, RB, active, t_min, mk.k0, mk.k1, cnt);
+            coop_bvh_item<BLOCK, COUNT>(S, sm, __float_as_int(IA.y), active, t_min, mk.k0, mk.k1, cnt);
         } else if (active) {
             float lim = best_t;
 #pragma unroll 1
