@@ -114,8 +114,16 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             need = true;
             if (h.rec >= 0) {
                 surf_t s;
-                finish_hit(P.S, wr, h, s);
-                const float4 m0 = __ldg(reinterpret_cast<const float4*>(P.S.materials + s.mat));
+                // does value(u,v,p) of this hit's texture read u,v?  (only image_texture does, PSC/surface_texture.h:19-30;
+                // a checker forwards u,v to its children, so it is treated as if it did)
+                const int mat_id = __float_as_int(__ldg(&P.S.recs[h.rec].b).w);
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(P.S.materials + mat_id));
+                bool want_uv = false;
+                if (__float_as_int(m0.y) >= 0 && __float_as_uint(m0.x) != RTNW_MAT_METAL && __float_as_uint(m0.x) != RTNW_MAT_DIELECTRIC) {
+                    const uint32_t tk = __float_as_uint(__ldg(reinterpret_cast<const float4*>(P.S.textures + __float_as_int(m0.y))).x);
+                    want_uv = tk == RTNW_TEX_IMAGE || tk == RTNW_TEX_CHECKER;
+                }
+                finish_hit(P.S, wr, h, s, want_uv);
                 if (__float_as_uint(m0.x) == RTNW_MAT_DIFFUSE_LIGHT) {  // the only material that emits; it never scatters
                     if (emit) L = L + T * texture_value(P.S, __float_as_int(m0.y), s.u, s.v, s.p);
                 } else if (depth < P.p.max_depth) {

@@ -328,25 +328,27 @@ __device__ __forceinline__ int key_face(hkey_t k) { return (int)(((uint32_t)k) &
 // bvh_node::hit's `box.hit(r,tmin,tmax)`, PSC/bvh.h:31 + PSC/aabb.h:33-49 with r.origin() (F2).  Selecting the
 // near/far plane by the sign of invD first is the reference's swap of (t0,t1); invD is a function of the ray only.
 __device__ __forceinline__ bool hit_aabb(float4 A, float4 B, f3 o, f3 inv, float t_lo, float t_hi) {
+    // `tmin = t0 > tmin ? t0 : tmin` is fmaxf(t0, tmin) whenever tmin is not NaN (a NaN t0, from 0 * inf, is ignored by
+    // both), likewise fminf for tmax; tmin starts finite, and a NaN tmax (closest_so_far after a NaN rectangle hit) makes
+    // the reference accept every box, which the last term reproduces.
     float lo_t = t_lo, hi_t = t_hi;
     {
         const bool neg = inv.x < 0.0f;
         const float t0 = ((neg ? A.w : A.x) - o.x) * inv.x, t1 = ((neg ? A.x : A.w) - o.x) * inv.x;
-        lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+        lo_t = fmaxf(t0, lo_t); hi_t = fminf(t1, hi_t);
     }
     {
         const bool neg = inv.y < 0.0f;
         const float t0 = ((neg ? B.x : A.y) - o.y) * inv.y, t1 = ((neg ? A.y : B.x) - o.y) * inv.y;
-        lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+        lo_t = fmaxf(t0, lo_t); hi_t = fminf(t1, hi_t);
     }
     {
         const bool neg = inv.z < 0.0f;
         const float t0 = ((neg ? B.y : A.z) - o.z) * inv.z, t1 = ((neg ? A.z : B.y) - o.z) * inv.z;
-        lo_t = t0 > lo_t ? t0 : lo_t; hi_t = t1 < hi_t ? t1 : hi_t;
+        lo_t = fmaxf(t0, lo_t); hi_t = fminf(t1, hi_t);
     }
-    return !(hi_t <= lo_t);
+    return !(hi_t <= lo_t) || (t_hi != t_hi);
 }
-
 __device__ __forceinline__ bool hit_aabb6(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, f3 o, f3 inv, float t_lo,
                                           float t_hi) {
     return hit_aabb(make_float4(mnx, mny, mnz, mxx), make_float4(mxy, mxz, 0.f, 0.f), o, inv, t_lo, t_hi);
@@ -413,12 +415,12 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
 #define RTNW_QN 6144  // node task stack
 #endif
 #ifndef RTNW_QL
-#define RTNW_QL 6144  // gate queue; flushed whenever fewer than 4*BLOCK slots are free
+#define RTNW_QL 4096  // gate queue (circular, power of two); node work pauses while fewer than 4*BLOCK slots are free
 #endif
 template <int BLOCK>
 struct coop_smem {
     static_assert(BLOCK <= 256 && BLOCK % 32 == 0, "a task carries its owner slot in 8 bits");
-    static_assert(RTNW_QL >= 8 * BLOCK && RTNW_QN >= 8 * BLOCK, "queues too small for the block");
+    static_assert(RTNW_QL >= 8 * BLOCK && (RTNW_QL & (RTNW_QL - 1)) == 0 && RTNW_QN >= 8 * BLOCK, "queues too small for the block");
     float4 ray_o[BLOCK];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
     float4 ray_d[BLOCK];  // d.xyz, w = dot(d,d)
     float4 ray_i[BLOCK];  // 1/d, w = time
@@ -426,71 +428,56 @@ struct coop_smem {
     hkey_t key[BLOCK];
     uint32_t q[RTNW_QN];
     uint32_t ql[RTNW_QL];
-    int n[2];             // stack height, double-buffered across rounds
-    int nl;
+    int n[2];             // node stack height, double-buffered across rounds
+    unsigned lh[2];       // gate queue head (consumed), double-buffered; counts up, index = value % RTNW_QL
+    unsigned lt;          // gate queue tail (produced)
     int overflow;         // a push did not fit (cannot happen for validated scenes); reported to the host
 };
 // task = owner slot (8 bits) | wide node index or gate index (24 bits)
 #define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 24) | (uint32_t)(idx))
 
-// every queued (ray, gate) pair: leaf->hit(r, tmin, tmax0) for the gate's leaves; all threads, then the queue is empty
-template <int BLOCK, bool COUNT>
-__device__ __forceinline__ void coop_flush_leaves(const scene_view& S, coop_smem<BLOCK>& sm, float t_min, uint32_t k0, uint32_t k1,
-                                                  trav_counters& cnt) {
-    const int tid = threadIdx.x;
-    const int nl = min(sm.nl, RTNW_QL);
-#pragma unroll 1
-    for (int q = tid; q < nl; q += BLOCK) {
-        const uint32_t task = sm.ql[q];
-        const int slot = (int)(task >> 24);
-        const int2 g = __ldg(&S.gates[task & 0xffffffu]);
-        const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
-        const uint4 mq = sm.mkey[slot];
-        ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
-        medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-        hkey_t k = test_leaf<COUNT>(S, g.x, r, rd.w, t_min, ro.w, mk, cnt);
-        if (g.y >= 0) {
-            const hkey_t k2 = test_leaf<COUNT>(S, g.y, r, rd.w, t_min, ro.w, mk, cnt);
-            if (k2 < k) k = k2;
-        }
-        if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
-    }
-    __syncthreads();
-    if (tid == 0) sm.nl = 0;
-    __syncthreads();
-}
-
 // Closest hit of the block's rays against the BVH item whose gate tree has root `root`.  Owners have already written
 // their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
+//
+// One loop of rounds, two barriers per round.  In a round the first ceil(take/32) warps each take one node task per
+// lane from the top of the stack; the remaining warps take one queued gate per lane (leaf->hit for its leaves), so
+// thin node rounds are filled with leaf work instead of idling at the barrier; when the stack is empty all warps
+// drain the gate queue.
 template <int BLOCK, bool COUNT>
 __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, bool active, float t_min,
                                               uint32_t k0, uint32_t k1, trav_counters& cnt) {
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
-    const unsigned lane = tid & 31u, lt = (1u << lane) - 1u;
-    if (tid < 2) sm.n[tid] = 0;
-    if (tid == 2) sm.nl = 0;
+    const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+    if (tid < 2) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
+    if (tid == 2) sm.lt = 0u;
     __syncthreads();
     {   // one task per ray: the root of the gate tree
         const unsigned b = __ballot_sync(FULL, active);
         int base = 0;
         if (lane == 0 && b) base = atomicAdd(&sm.n[0], __popc(b));
         base = __shfl_sync(FULL, base, 0);
-        if (active) sm.q[base + __popc(b & lt)] = RTNW_TASK(tid, root);
+        if (active) sm.q[base + __popc(b & lt_mask)] = RTNW_TASK(tid, root);
     }
     __syncthreads();
 #pragma unroll 1
     for (int round = 0;; ++round) {
         const int n = sm.n[round & 1];
-        if (n == 0) break;
-        const int take = min(n, BLOCK), base = n - take;
-        int* n_nxt = &sm.n[(round + 1) & 1];
+        const unsigned lh = sm.lh[round & 1], ltail = sm.lt;
+        const int queued = (int)(ltail - lh);
+        if (n == 0 && queued == 0) break;
+        const int take = (queued > RTNW_QL - 4 * BLOCK) ? 0 : min(n, BLOCK);  // pause node work while the gate queue is nearly full
+        const int base = n - take;
+        const int node_threads = (take + 31) & ~31;
+        const int drain = min(queued, BLOCK - node_threads);
         uint32_t task = 0;
         if (tid < take) task = sm.q[base + tid];
-        if (tid == 0) *n_nxt = base;  // pop; this round's pushes land on top of what remains
+        else if (tid >= node_threads && tid - node_threads < drain) task = sm.ql[(lh + (unsigned)(tid - node_threads)) & (RTNW_QL - 1)];
+        if (tid == 0) { sm.n[(round + 1) & 1] = base; sm.lh[(round + 1) & 1] = lh + (unsigned)drain; }  // pop both
         __syncthreads();
-        if ((tid & ~31) < take) {  // warps without a task this round go straight to the barrier
-            const int slot = (int)(task >> 24);
+        const int slot = (int)(task >> 24);
+        if (tid < node_threads) {
+            // ---- node warps: test the <= 4 child boxes of one wide node per lane, push what passed
             int ref[4] = {RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE};
             bool pass[4] = {false, false, false, false};
             if (tid < take) {
@@ -506,7 +493,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
                 pass[3] = ref[3] != RTNW_REF_NONE && hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, ro.w);
                 if (COUNT) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
             }
-            // warp-aggregated appends: wide nodes back onto the stack, gates to the leaf queue
+            // warp-aggregated appends: wide nodes back onto the stack, gates to the gate queue
             unsigned bn[4], bl[4];
             int tn = 0, tl = 0;
 #pragma unroll
@@ -515,33 +502,47 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
                 bl[j] = __ballot_sync(FULL, pass[j] && ref[j] < 0);
                 tn += __popc(bn[j]); tl += __popc(bl[j]);
             }
-            int base_n = 0, base_l = 0;
+            int base_n = 0;
+            unsigned base_l = 0;
             if (lane == 0) {
-                if (tn) base_n = atomicAdd(n_nxt, tn);
-                if (tl) base_l = atomicAdd(&sm.nl, tl);
+                if (tn) base_n = atomicAdd(&sm.n[(round + 1) & 1], tn);
+                if (tl) base_l = atomicAdd(&sm.lt, (unsigned)tl);
             }
             base_n = __shfl_sync(FULL, base_n, 0);
             base_l = __shfl_sync(FULL, base_l, 0);
-            bool ok = true;
+            bool ok = (int)(base_l + (unsigned)tl - lh) <= RTNW_QL;  // never laps the unconsumed part of the ring
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (pass[j]) {
                     if (ref[j] >= 0) {
-                        const int at = base_n + __popc(bn[j] & lt);
+                        const int at = base_n + __popc(bn[j] & lt_mask);
                         if (at < RTNW_QN) sm.q[at] = RTNW_TASK(slot, ref[j]); else ok = false;
-                    } else {
-                        const int at = base_l + __popc(bl[j] & lt);
-                        if (at < RTNW_QL) sm.ql[at] = RTNW_TASK(slot, ~ref[j]); else ok = false;
+                    } else if (ok) {
+                        sm.ql[(base_l + (unsigned)__popc(bl[j] & lt_mask)) & (RTNW_QL - 1)] = RTNW_TASK(slot, ~ref[j]);
                     }
                 }
-                base_n += __popc(bn[j]); base_l += __popc(bl[j]);
+                base_n += __popc(bn[j]); base_l += (unsigned)__popc(bl[j]);
             }
             if (!ok) sm.overflow = 1;
+        } else if (tid - node_threads < drain) {
+            // ---- gate lanes: leaf->hit(r, tmin, tmax0) for the one or two leaves the gate guards
+            const int2 g = __ldg(&S.gates[task & 0xffffffu]);
+            const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
+            const uint4 mq = sm.mkey[slot];
+            ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+            medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
+            hkey_t k = RTNW_KEY_NONE;
+#pragma unroll 1
+            for (int w = 0; w < 2; ++w) {  // one copy of the leaf code
+                const int leaf = w ? g.y : g.x;
+                if (leaf < 0) break;
+                const hkey_t k2 = test_leaf<COUNT>(S, leaf, r, rd.w, t_min, ro.w, mk, cnt);
+                if (k2 < k) k = k2;
+            }
+            if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
         }
         __syncthreads();
-        if (sm.nl > RTNW_QL - 4 * BLOCK) coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
     }
-    coop_flush_leaves<BLOCK, COUNT>(S, sm, t_min, k0, k1, cnt);
 }
 
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
@@ -608,7 +609,9 @@ struct surf_t { f3 p, n; float u, v; int mat; };
 
 // Rebuild the hit_record of the winning record: p / normal / uv are pure functions of (ray, primitive, t), so the
 // traversal only tracks (t, record) and the record is evaluated once here.
-__device__ __forceinline__ void finish_hit(const scene_view& S, const ray_t& wr, const hit_t& h, surf_t& s) {
+// want_uv: the spherical (u,v) of PSC/hitable.h:14-19 costs an atan2f, an asinf and two double divisions, and only
+// image_texture::value reads u,v; the renderer asks for it only when the hit material's texture is an image.
+__device__ __forceinline__ void finish_hit(const scene_view& S, const ray_t& wr, const hit_t& h, surf_t& s, bool want_uv = true) {
     const float4 A = __ldg(&S.recs[h.rec].a), B = __ldg(&S.recs[h.rec].b);
     const uint32_t tag = __float_as_uint(B.z);
     const uint32_t kind = tag & 15u, chain = tag >> 8;
@@ -623,7 +626,7 @@ __device__ __forceinline__ void finish_hit(const scene_view& S, const ray_t& wr,
     switch (kind) {
         case K_SPHERE: {
             s.n = (s.p - mk3(A.x, A.y, A.z)) / A.w;
-            get_sphere_uv(s.n, s.u, s.v);
+            if (want_uv) get_sphere_uv(s.n, s.u, s.v);
             break;
         }
         case K_MSPHERE: {
