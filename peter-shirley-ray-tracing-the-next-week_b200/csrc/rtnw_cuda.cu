@@ -613,7 +613,7 @@ struct stream_builder {
         }
         cur_item_xf = 0;
         push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_END, 0, 0, 0), 0, -1);
-        if (recs.size() >= (1u << 24) || gates.size() >= (1u << 24) || wnodes.size() / 8 >= (1u << 24)) return bad("scene exceeds 2^24 records");
+        if (recs.size() >= (1u << 24) || gates.size() >= (1u << RTNW_IDX_BITS) || wnodes.size() / 8 >= (1u << RTNW_IDX_BITS)) return bad("scene exceeds the record / gate index range");
         if (3 * (max_wide_depth + 1) + 1 > RTNW_QN / RTNW_BLOCK) return bad("gate tree deeper than the cooperative task stack allows");
         if (gate_leaves.empty()) gate_leaves.push_back(make_int2(-1, -1));
         if (wnodes.empty()) wnodes.resize(8, make_float4(0, 0, 0, 0));

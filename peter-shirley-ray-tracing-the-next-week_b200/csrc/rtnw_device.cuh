@@ -419,7 +419,7 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
 #endif
 template <int BLOCK>
 struct coop_smem {
-    static_assert(BLOCK <= 256 && BLOCK % 32 == 0, "a task carries its owner slot in 8 bits");
+    static_assert(BLOCK <= 512 && BLOCK % 32 == 0, "a task carries its owner slot in 9 bits");
     static_assert(RTNW_QL >= 8 * BLOCK && (RTNW_QL & (RTNW_QL - 1)) == 0 && RTNW_QN >= 8 * BLOCK, "queues too small for the block");
     float4 ray_o[BLOCK];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
     float4 ray_d[BLOCK];  // d.xyz, w = dot(d,d)
@@ -433,8 +433,11 @@ struct coop_smem {
     unsigned lt;          // gate queue tail (produced)
     int overflow;         // a push did not fit (cannot happen for validated scenes); reported to the host
 };
-// task = owner slot (8 bits) | wide node index or gate index (24 bits)
-#define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 24) | (uint32_t)(idx))
+// task = owner slot (9 bits) | wide node index or gate index (23 bits)
+#define RTNW_IDX_BITS 23
+#define RTNW_TASK(slot, idx) (((uint32_t)(slot) << RTNW_IDX_BITS) | (uint32_t)(idx))
+#define RTNW_TASK_SLOT(task) ((int)((task) >> RTNW_IDX_BITS))
+#define RTNW_TASK_IDX(task) ((task) & ((1u << RTNW_IDX_BITS) - 1u))
 
 // Closest hit of the block's rays against the BVH item whose gate tree has root `root`.  Owners have already written
 // their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
@@ -475,13 +478,13 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         else if (tid >= node_threads && tid - node_threads < drain) task = sm.ql[(lh + (unsigned)(tid - node_threads)) & (RTNW_QL - 1)];
         if (tid == 0) { sm.n[(round + 1) & 1] = base; sm.lh[(round + 1) & 1] = lh + (unsigned)drain; }  // pop both
         __syncthreads();
-        const int slot = (int)(task >> 24);
+        const int slot = RTNW_TASK_SLOT(task);
         if (tid < node_threads) {
             // ---- node warps: test the <= 4 child boxes of one wide node per lane, push what passed
             int ref[4] = {RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE};
             bool pass[4] = {false, false, false, false};
             if (tid < take) {
-                const float4* N = S.wnodes + 8 * (size_t)(task & 0xffffffu);
+                const float4* N = S.wnodes + 8 * (size_t)RTNW_TASK_IDX(task);
                 const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
                 const float4 rf = __ldg(N + 6);
                 const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
@@ -526,7 +529,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
             if (!ok) sm.overflow = 1;
         } else if (tid - node_threads < drain) {
             // ---- gate lanes: leaf->hit(r, tmin, tmax0) for the one or two leaves the gate guards
-            const int2 g = __ldg(&S.gates[task & 0xffffffu]);
+            const int2 g = __ldg(&S.gates[RTNW_TASK_IDX(task)]);
             const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
             const uint4 mq = sm.mkey[slot];
             ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
