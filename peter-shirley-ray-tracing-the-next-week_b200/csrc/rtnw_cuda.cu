@@ -503,9 +503,12 @@ struct stream_builder {
                 right_area[q - lo] = half_area(rmin, rmax);
             }
             float lmin[3], lmax[3];
+            // keep both sides at least an eighth of the range: nested boxes would otherwise be peeled off one per level
+            const size_t margin = (hi - lo) / 8;
             for (size_t q = lo; q + 1 < hi; ++q) {
                 if (q == lo) { for (int a = 0; a < 3; ++a) { lmin[a] = gates[ids[q]].bmin[a]; lmax[a] = gates[ids[q]].bmax[a]; } }
                 else for (int a = 0; a < 3; ++a) { lmin[a] = std::fmin(lmin[a], gates[ids[q]].bmin[a]); lmax[a] = std::fmax(lmax[a], gates[ids[q]].bmax[a]); }
+                if (q + 1 - lo < margin || hi - q - 1 < margin) continue;
                 const double cost = half_area(lmin, lmax) * (double)(q - lo + 1) + right_area[q + 1 - lo] * (double)(hi - q - 1);
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = q + 1; }
             }
@@ -551,15 +554,18 @@ struct stream_builder {
         wnodes[8 * me + 6] = make_float4(bits(ref[0]), bits(ref[1]), bits(ref[2]), bits(ref[3]));
         return (int)me;
     }
-    // one BVH item: returns the root wide node
-    bool emit_bvh_item(const rtnw_item& it, int& root_out) {
+    // one BVH item: returns the root wide node and the depth of its gate tree
+    bool emit_bvh_item(const rtnw_item& it, int& root_out, int& depth_out) {
         std::vector<int> mine;
         if (!collect_gates(it.first, it.bmin, it.bmax, 0, mine)) return false;
         if (mine.empty()) return bad("BVH without leaves");
         std::vector<bin_node> bt;
         bt.reserve(2 * mine.size());
         const int broot = build_binary(mine, 0, mine.size(), bt);
+        max_wide_depth = 0;
         root_out = emit_wide(bt, broot, 0);
+        depth_out = max_wide_depth + 1;
+        if (RTNW_BLOCK + 3 * depth_out + 8 > RTNW_QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
         return true;
     }
 
@@ -603,9 +609,10 @@ struct stream_builder {
             if (it.kind == RTNW_ITEM_PRIMS) {
                 if (!emit_prims(it.first, it.count, true, false)) return false;
             } else if (it.kind == RTNW_ITEM_BVH) {
-                int wroot = 0;
-                if (!emit_bvh_item(it, wroot)) return false;  // leaves -> record stream, gates + gate tree -> side tables
+                int wroot = 0, wdepth = 0;
+                if (!emit_bvh_item(it, wroot, wdepth)) return false;  // leaves -> record stream, gates + gate tree -> side tables
                 recs[at].a.y = bits(wroot);
+                recs[at].a.z = bits(wdepth);
             } else {
                 return bad("unknown item kind");
             }
@@ -614,7 +621,6 @@ struct stream_builder {
         cur_item_xf = 0;
         push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_END, 0, 0, 0), 0, -1);
         if (recs.size() >= (1u << 24) || gates.size() >= (1u << RTNW_IDX_BITS) || wnodes.size() / 8 >= (1u << RTNW_IDX_BITS)) return bad("scene exceeds the record / gate index range");
-        if (3 * (max_wide_depth + 1) + 1 > RTNW_QN / RTNW_BLOCK) return bad("gate tree deeper than the cooperative task stack allows");
         if (gate_leaves.empty()) gate_leaves.push_back(make_int2(-1, -1));
         if (wnodes.empty()) wnodes.resize(8, make_float4(0, 0, 0, 0));
         return true;

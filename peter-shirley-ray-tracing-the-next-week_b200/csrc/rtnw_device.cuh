@@ -409,8 +409,11 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
 // Tasks are uniform and any thread can take any of them: a node task (ray, wide node) tests the node's <= 4 child
 // boxes and pushes the children that passed — wide nodes back on the stack, gates to the leaf queue; a gate task runs
 // leaf->hit(r, tmin, tmax0) for the gate's one or two leaves.  Candidates are merged per ray with atomicMin on the
-// 64-bit key.  The stack is served LIFO, BLOCK tasks at a time: a round pops <= BLOCK tasks and pushes <= 4*BLOCK
-// children one level deeper, so it never holds more than BLOCK*(3*depth+1) tasks (validated at upload).
+// 64-bit key.  The stack is served LIFO.  A popped task frees one slot and pushes at most four, so a round that pops
+// `take` tasks needs 3*take free slots; `take` is BLOCK while there is room and shrinks as the stack fills, always
+// leaving 3*depth slots in reserve: with take = 1 the traversal is a plain depth-first walk, which needs at most
+// 3*(depth - d) slots above a task at depth d.  Hence the stack cannot overflow for a tree of any depth, and the usual
+// case (room for everything) runs BLOCK tasks wide.
 #ifndef RTNW_QN
 #define RTNW_QN 6144  // node task stack
 #endif
@@ -447,8 +450,8 @@ struct coop_smem {
 // thin node rounds are filled with leaf work instead of idling at the barrier; when the stack is empty all warps
 // drain the gate queue.
 template <int BLOCK, bool COUNT>
-__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, bool active, float t_min,
-                                              uint32_t k0, uint32_t k1, trav_counters& cnt) {
+__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, int tree_depth, bool active,
+                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt) {
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
@@ -469,7 +472,9 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         const unsigned lh = sm.lh[round & 1], ltail = sm.lt;
         const int queued = (int)(ltail - lh);
         if (n == 0 && queued == 0) break;
-        const int take = (queued > RTNW_QL - 4 * BLOCK) ? 0 : min(n, BLOCK);  // pause node work while the gate queue is nearly full
+        // node tasks this round: none while the gate ring is nearly full; otherwise as many as the stack has room for
+        const int room = (RTNW_QN - n - 3 * tree_depth) / 3;
+        const int take = (queued > RTNW_QL - 4 * BLOCK) ? 0 : min(min(n, BLOCK), max(room, 1));
         const int base = n - take;
         const int node_threads = (take + 31) & ~31;
         const int drain = min(queued, BLOCK - node_threads);
@@ -571,7 +576,7 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
             sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
             sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
             sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-            coop_bvh_item<BLOCK, COUNT>(S, sm, __float_as_int(IA.y), active, t_min, mk.k0, mk.k1, cnt);
+            coop_bvh_item<BLOCK, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt);
         } else if (active) {
             float lim = best_t;
 #pragma unroll 1

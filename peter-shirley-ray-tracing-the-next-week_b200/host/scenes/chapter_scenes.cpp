@@ -209,6 +209,17 @@ hitable* two_spheres() {
     return w.as_list();
 }
 
+// Not a reference scene: a queue stress fixture for the tests.  600 concentric glass/diffuse shells, so a ray aimed at the
+// centre passes every bounding box of any bvh_node built over them (hundreds of leaves per ray, all with nearly equal t).
+hitable* stress_shells() {
+    pool w(600);
+    for (int k = 0; k < 600; ++k) {
+        material* m = (k % 3 == 0) ? static_cast<material*>(new dielectric(1.5f)) : matte(0.2f + 0.001f * k, 0.5f, 0.9f - 0.001f * k);
+        w.add(new sphere(vec3(0.01f * (k % 7), 0.02f * (k % 5), 0.0f), 1.0f + 0.01f * k, m));
+    }
+    return w.as_list();
+}
+
 hitable* wrap_in_bvh(hitable* flat_list, float t0, float t1) {
     hitable_list* l = static_cast<hitable_list*>(flat_list);
     return new bvh_node(l->list, l->list_size, t0, t1);

@@ -30,6 +30,7 @@ hitable* final_northstar();        // config 5N: nb = 32 floor boxes in a bvh_no
 hitable* simple_light();           // PSC/main.cpp:122-133
 hitable* two_spheres();            // PSC/main.cpp:99-110
 hitable* earth();                  // PSC/main.cpp:87-97 with the synthetic RGB8 image
+hitable* stress_shells();          // test fixture (not in the reference): 600 nested shells, every ray passes every box
 hitable* wrap_in_bvh(hitable* flat_list, float t0, float t1);  // `new bvh_node(list->list, list->list_size, t0, t1)`
 
 // deterministic 1024x512 RGB8 stand-in for picture.png (the shipped PNG is RGBA and mis-strided)
