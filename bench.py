@@ -236,7 +236,9 @@ def main():
     e2e_kernel_ms = []
 
     def e2e_step():
+        _t0 = time.perf_counter()
         s2 = ctx.upload(hs.desc_ptr)  # H2D of every scene table
+        _t1 = time.perf_counter()
         if dist is None:
             _, st2 = s2.render(cam, params, out=host_np)  # render + D2H into pinned host memory
             e2e_kernel_ms.append(st2.kernel_ms)
@@ -246,7 +248,11 @@ def main():
             dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 host_accum.copy_(accum, non_blocking=False)
+        _t2 = time.perf_counter()
         s2.close()
+        if os.environ.get("RTNW_BENCH_DEBUG"):
+            print(f"e2e step: upload {1e3 * (_t1 - _t0):.2f} render {1e3 * (_t2 - _t1):.2f} close {1e3 * (time.perf_counter() - _t2):.2f} ms "
+                  f"kernel {st2.kernel_ms:.2f} total {st2.total_ms:.2f}", file=sys.stderr)
 
     for _ in range(2):
         e2e_step()

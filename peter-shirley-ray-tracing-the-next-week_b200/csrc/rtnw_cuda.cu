@@ -319,11 +319,16 @@ struct rtnw_ctx {
     size_t accum_floats = 0;
     unsigned long long* ctr = nullptr;  // 4 device counters
     int blocks_per_sm[2] = {0, 0};
+    // freed scene slabs are kept for the next upload (cudaMalloc/cudaFree synchronise the device and can take
+    // milliseconds to hundreds of milliseconds in a process that also hosts another allocator)
+    void* spare_slab[2] = {nullptr, nullptr};
+    size_t spare_bytes[2] = {0, 0};
 };
 
 struct rtnw_scene {
     scene_view view;
     void* slab = nullptr;  // one allocation holding every table
+    size_t slab_bytes = 0;
     int32_t n_leaf_ids = 0;
 };
 
@@ -745,6 +750,7 @@ int rtnw_ctx_destroy(rtnw_ctx* c) {
     if (!c) return RTNW_OK;
     cudaSetDevice(c->device);
     if (c->accum) cudaFree(c->accum);
+    for (int q = 0; q < 2; ++q) if (c->spare_slab[q]) cudaFree(c->spare_slab[q]);
     if (c->ctr) cudaFree(c->ctr);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -835,7 +841,18 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     if (sz_img) std::memcpy(host.data() + o_img, desc->images, sz_img);
 
     rtnw_scene* s = new rtnw_scene();
-    cudaError_t e = cudaMalloc(&s->slab, off);
+    cudaError_t e = cudaSuccess;
+    for (int q = 0; q < 2 && !s->slab; ++q)
+        if (ctx->spare_slab[q] && ctx->spare_bytes[q] >= off) {
+            s->slab = ctx->spare_slab[q];
+            s->slab_bytes = ctx->spare_bytes[q];
+            ctx->spare_slab[q] = nullptr;
+            ctx->spare_bytes[q] = 0;
+        }
+    if (!s->slab) {
+        e = cudaMalloc(&s->slab, off);
+        s->slab_bytes = off;
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->slab, host.data(), off, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
@@ -864,7 +881,15 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
 
 int rtnw_scene_free(rtnw_ctx* ctx, rtnw_scene* scene) {
     if (!scene) return RTNW_OK;
-    if (ctx) cudaSetDevice(ctx->device);
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        for (int q = 0; q < 2 && scene->slab; ++q)
+            if (!ctx->spare_slab[q]) {
+                ctx->spare_slab[q] = scene->slab;
+                ctx->spare_bytes[q] = scene->slab_bytes;
+                scene->slab = nullptr;
+            }
+    }
     if (scene->slab) cudaFree(scene->slab);
     delete scene;
     return RTNW_OK;
