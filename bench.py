@@ -180,8 +180,14 @@ def main():
     ds = ctx.upload(hs.desc_ptr)
     nx, ny, ns = WORKLOAD["nx"], WORKLOAD["ny"], WORKLOAD["ns"]
     cam = hs.camera(nx, ny)
-    begin, my_ns, stride = mg.sample_partition(ns, world, rank)  # samples rank, rank+world, ...
-    params = hs.params(nx=nx, ny=ny, ns=my_ns, seed=SEED, sample_begin=begin, sample_stride=stride, flags_extra=args.flags)
+    plan = mg.partition_plan(ns, nx * ny, world, rank)  # evenly divisible samples by sample index, the rest by pixel
+
+    def launch_params(launch, first):
+        extra = args.flags | (rtnw.F_ACCUMULATE if (launch["accumulate"] or not first) else 0)
+        return hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=SEED, sample_begin=launch["sample_begin"],
+                         sample_stride=launch["sample_stride"], flags_extra=extra, pixel_begin=launch["pixel_begin"],
+                         pixel_stride=launch["pixel_stride"], pixel_count=launch["pixel_count"])
+    params = launch_params(plan[0], True)  # world == 1: the whole frame in one launch
     accum = torch.empty(ny, nx, 3, dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
@@ -194,10 +200,17 @@ def main():
     last = {}
 
     def step():
-        def render(b, c, s):
-            last["st"] = ds.render_device(cam, params, accum.data_ptr(), stream.cuda_stream)
-        mg.render_partitioned(render, accum, ns, dist=dist, dst=0)  # k_render on every rank, then one NCCL reduce(sum)
-        return last["st"]
+        last["rays"], last["kernel_ms"], last["launches"] = 0, 0.0, 0
+
+        def render(**launch):
+            extra = args.flags | (rtnw.F_ACCUMULATE if launch["accumulate"] else 0)
+            p = hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=SEED, sample_begin=launch["sample_begin"],
+                          sample_stride=launch["sample_stride"], flags_extra=extra, pixel_begin=launch["pixel_begin"],
+                          pixel_stride=launch["pixel_stride"], pixel_count=launch["pixel_count"])
+            st = ds.render_device(cam, p, accum.data_ptr(), stream.cuda_stream)
+            last["rays"] += st.rays; last["kernel_ms"] += st.kernel_ms; last["launches"] += 1
+        mg.render_partitioned(render, accum, ns, dist=dist, dst=0)  # k_render launches of this rank, then one NCCL reduce(sum)
+        return last
 
     for _ in range(args.warmup):
         step()
@@ -213,8 +226,9 @@ def main():
         a.record(stream)
         st = step()
         b.record(stream)
-        rays += st.rays
-        kernel_ms.append(st.kernel_ms)
+        rays += st["rays"]
+        kernel_ms.append(st["kernel_ms"])
+        launches_per_step = st["launches"]
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     clocks = sampler.result()
@@ -243,16 +257,23 @@ def main():
             _, st2 = s2.render(cam, params, out=host_np)  # render + D2H into pinned host memory
             e2e_kernel_ms.append(st2.kernel_ms)
         else:
-            st2 = s2.render_device(cam, params, accum.data_ptr(), stream.cuda_stream)
-            e2e_kernel_ms.append(st2.kernel_ms)
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            tot = {"ms": 0.0}
+
+            def render2(**launch):
+                extra = args.flags | (rtnw.F_ACCUMULATE if launch["accumulate"] else 0)
+                p = hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=SEED, sample_begin=launch["sample_begin"],
+                              sample_stride=launch["sample_stride"], flags_extra=extra, pixel_begin=launch["pixel_begin"],
+                              pixel_stride=launch["pixel_stride"], pixel_count=launch["pixel_count"])
+                tot["ms"] += s2.render_device(cam, p, accum.data_ptr(), stream.cuda_stream).kernel_ms
+            mg.render_partitioned(render2, accum, ns, dist=dist, dst=0)
+            e2e_kernel_ms.append(tot["ms"])
             if rank == 0:
                 host_accum.copy_(accum, non_blocking=False)
         _t2 = time.perf_counter()
         s2.close()
         if os.environ.get("RTNW_BENCH_DEBUG"):
             print(f"e2e step: upload {1e3 * (_t1 - _t0):.2f} render {1e3 * (_t2 - _t1):.2f} close {1e3 * (time.perf_counter() - _t2):.2f} ms "
-                  f"kernel {st2.kernel_ms:.2f} total {st2.total_ms:.2f}", file=sys.stderr)
+                  f"kernel {e2e_kernel_ms[-1]:.2f}", file=sys.stderr)
 
     for _ in range(2):
         e2e_step()
@@ -286,7 +307,7 @@ def main():
         except Exception:
             pass
         info = ctx.info()
-        kernel_s = sum(kernel_ms) / 1e3 / len(kernel_ms)
+        kernel_s = sum(kernel_ms) / 1e3 / len(kernel_ms)  # all k_render launches of one step on rank 0
         rays_per_launch = rays / args.steps
         f_ray = flops_per_ray(counts)
         sm_mhz = clocks["sm_mhz"] or (info["clock_khz"] / 1e3)
@@ -301,14 +322,14 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "final_northstar 1000x1000x100spp (config 5N: BVH over 1024 floor boxes + "
                                    "translate(rotate_y(BVH over 1000 spheres)) + media + perlin + image texture)",
-                       "paths_per_step": paths_per_step, "partition": f"spp split over {world} GPU(s), 1 NCCL reduce",
+                       "paths_per_step": paths_per_step, "partition": f"spp split over {world} GPU(s) (left-over samples by interleaved pixels), 1 NCCL reduce",
                        "l2": "flushed between timed steps (256 MiB write)", "traversal": "narrowed" if args.flags & 4 else "reference-exact",
                        "seed": SEED},
             "mrays_per_s": mrays, "rays_per_path": tot_rays.item() / (paths_per_step * args.steps),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": desc_bytes * world,
                     "d2h_bytes_per_step": nx * ny * 3 * 4, "ms_per_step": 1e3 * e2e_s.item() / args.steps,
                     "kernel_ms_per_step": sum(e2e_kernel_ms[-args.steps:]) / args.steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch, ncu --set full capture

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RTNW_ABI_VERSION 3
+#define RTNW_ABI_VERSION 4
 
 enum rtnw_status {
     RTNW_OK = 0,
@@ -156,6 +156,7 @@ enum rtnw_background { RTNW_BG_BLACK = 0 /* PSC/main.cpp:44 */, RTNW_BG_SKY = 1 
 #define RTNW_F_CULL_NARROW   4u  /* reserved (accepted and ignored): the cooperative BVH traversal always tests exactly the nodes
                                     and leaves the reference's un-narrowed bvh_node::hit tests */
 #define RTNW_F_COUNTERS      8u  /* fill the optional work counters in rtnw_stats */
+#define RTNW_F_ACCUMULATE   16u  /* add this call's pixel sums to accum_rgb instead of overwriting (rtnw_render_device only) */
 
 typedef struct rtnw_render_params {
     int32_t nx, ny;
@@ -168,6 +169,10 @@ typedef struct rtnw_render_params {
     uint32_t background;    /* rtnw_background */
     uint32_t flags;         /* RTNW_F_* */
     uint64_t seed;          /* Philox key; the sample stream of a path is a function of (seed, pixel, sample) only */
+    /* pixel subset of this call: pixels p = pixel_begin + k*pixel_stride, k in [0, pixel_count); p = j*nx + i.
+     * pixel_count == 0 means every pixel (begin 0, stride 1).  Pixels outside the subset are left untouched.  Used by
+     * the multi-GPU split for the samples that do not divide evenly among the ranks. */
+    int32_t pixel_begin, pixel_stride, pixel_count, pad;
 } rtnw_render_params;
 
 typedef struct rtnw_stats {

@@ -623,6 +623,10 @@ int rtnw_oracle_render(const rtnw_scene_desc* d, const rtnw_camera* cam, const r
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int j = P->ny - 1; j >= 0; j--) {
         for (int i = 0; i < P->nx; i++) {
+            if (P->pixel_count > 0) { /* pixel subset begin + k*stride, k < count */
+                const int rel = j * P->nx + i - P->pixel_begin;
+                if (rel < 0 || rel % P->pixel_stride != 0 || rel / P->pixel_stride >= P->pixel_count) continue;
+            }
             vec3 col = V(0, 0, 0);
             for (int k = 0; k < P->sample_count; k++) {
                 const int s = P->sample_begin + k * P->sample_stride;
@@ -634,12 +638,15 @@ int rtnw_oracle_render(const rtnw_scene_desc* d, const rtnw_camera* cam, const r
                         if (!(temp.e[q] == temp.e[q])) temp.e[q] = 0;
                 col = vadd(col, temp);
             }
-            for (int q = 0; q < 3; ++q) accum[3 * ((size_t)j * P->nx + i) + q] = col.e[q];
+            for (int q = 0; q < 3; ++q) {
+                float* dst = &accum[3 * ((size_t)j * P->nx + i) + q];
+                *dst = (P->flags & RTNW_F_ACCUMULATE) ? *dst + col.e[q] : col.e[q];
+            }
         }
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (stats) {
-        stats[0] = (double)P->nx * P->ny * P->sample_count;
+        stats[0] = (double)(P->pixel_count > 0 ? P->pixel_count : P->nx * P->ny) * P->sample_count;
         stats[1] = (double)g.rays;
         stats[2] = (double)g.box_tests;
         stats[3] = (double)g.prim_tests;

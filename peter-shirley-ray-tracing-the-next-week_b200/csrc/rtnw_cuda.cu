@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int nx = P.p.nx, ny = P.p.ny;
-    const unsigned long long npix = (unsigned long long)nx * (unsigned long long)ny;
+    const unsigned long long npix = (unsigned long long)P.p.pixel_count;  // render_core fills in the default subset
+    const bool accumulate = (P.p.flags & RTNW_F_ACCUMULATE) != 0;
     const uint32_t k0 = (uint32_t)P.p.seed, k1 = (uint32_t)(P.p.seed >> 32);
     const bool emit = (P.p.flags & RTNW_F_EMIT) != 0;
     const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
         // ---- next sample of the pixel, or next pixel, PSC/main.cpp:299-308
         if (alive && need && pix >= 0 && k == P.p.sample_count) {
             float* dst = P.accum + 3ull * (unsigned long long)pix;
-            dst[0] = col.x; dst[1] = col.y; dst[2] = col.z;
+            if (accumulate) { dst[0] += col.x; dst[1] += col.y; dst[2] += col.z; }
+            else { dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; }
             pix = -1;
         }
         const bool want = alive && need && pix < 0;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             if (want) {
                 const unsigned long long mine = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
                 if (mine >= npix) alive = false;
-                else { pix = (int)mine; k = 0; col = mk3(0.f, 0.f, 0.f); }
+                else { pix = P.p.pixel_begin + (int)mine * P.p.pixel_stride; k = 0; col = mk3(0.f, 0.f, 0.f); }
             }
         }
         if (__syncthreads_count(alive) == 0) break;
@@ -649,7 +651,7 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
         if (bps < 1) bps = 1;
     }
     int blocks = ctx->sm_count * bps;
-    const long long warps_needed = ((long long)a.p.nx * a.p.ny + 31) / 32;
+    const long long warps_needed = ((long long)a.p.pixel_count + 31) / 32;
     const long long blocks_needed = (warps_needed * 32 + RTNW_BLOCK - 1) / RTNW_BLOCK;
     if (blocks_needed < blocks) blocks = (int)blocks_needed;
     if (const char* e = getenv("RTNW_GRID_BLOCKS")) { const int v = atoi(e); if (v > 0) blocks = v; }
@@ -664,6 +666,9 @@ int validate_params(const rtnw_render_params* p) {
     if (p->sample_count <= 0 || p->sample_stride <= 0 || p->sample_begin < 0) return fail(RTNW_ERR_INVALID, "bad sample range");
     if (p->max_depth < 0) return fail(RTNW_ERR_INVALID, "bad max_depth");
     if (p->background > RTNW_BG_SKY) return fail(RTNW_ERR_INVALID, "bad background");
+    if (p->pixel_count < 0 || (p->pixel_count > 0 && (p->pixel_begin < 0 || p->pixel_stride < 1 ||
+        (long long)p->pixel_begin + (long long)(p->pixel_count - 1) * p->pixel_stride >= (long long)p->nx * p->ny)))
+        return fail(RTNW_ERR_INVALID, "bad pixel subset");
     return RTNW_OK;
 }
 
@@ -674,6 +679,7 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     a.S = scene->view;
     a.cam = *cam;
     a.p = *p;
+    if (a.p.pixel_count == 0) { a.p.pixel_begin = 0; a.p.pixel_stride = 1; a.p.pixel_count = p->nx * p->ny; }
     a.accum = accum_dev;
     a.ctr = ctx->ctr;
     CUDA_TRY(cudaMemsetAsync(ctx->ctr, 0, 8 * sizeof(unsigned long long), st));
@@ -687,7 +693,7 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     if (h[4]) return fail(RTNW_ERR_UNSUPPORTED, "BVH task stack overflow: the tree is deeper than RTNW_QN/RTNW_BLOCK - 1 levels");
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
-        stats->paths = (uint64_t)p->nx * p->ny * p->sample_count;
+        stats->paths = (uint64_t)a.p.pixel_count * p->sample_count;
         stats->rays = h[1];
         stats->box_tests = h[2];
         stats->prim_tests = h[3];
@@ -911,6 +917,8 @@ int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     if (rc != RTNW_OK) return rc;
     if (!scene || !cam || !accum_rgb) return fail(RTNW_ERR_INVALID, "null argument");
     if ((rc = validate_params(params)) != RTNW_OK) return rc;
+    if (params->pixel_count != 0 || (params->flags & RTNW_F_ACCUMULATE))
+        return fail(RTNW_ERR_INVALID, "pixel subsets / RTNW_F_ACCUMULATE need rtnw_render_device (the host entry point returns whole images)");
     const size_t floats = (size_t)params->nx * params->ny * 3;
     if (ctx->accum_floats < floats) {
         if (ctx->accum) cudaFree(ctx->accum);

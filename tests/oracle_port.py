@@ -43,9 +43,10 @@ def trace(rtnw, desc, rays, t_min=0.001, t_max=None, seed=1):
     return out
 
 
-def render(rtnw, desc, cam, params):
-    """returns (sums[ny,nx,3], stats dict)"""
-    out = np.zeros((params.ny, params.nx, 3), dtype=np.float32)
+def render(rtnw, desc, cam, params, out=None):
+    """returns (sums[ny,nx,3], stats dict); pass `out` to accumulate into / keep untouched pixels of an existing image"""
+    if out is None:
+        out = np.zeros((params.ny, params.nx, 3), dtype=np.float32)
     st = np.zeros(5, dtype=np.float64)
     rc = lib().rtnw_oracle_render(_desc_ptr(desc), C.cast(C.pointer(cam), C.c_void_p), C.cast(C.pointer(params), C.c_void_p),
                                   out.ctypes.data, st.ctypes.data)

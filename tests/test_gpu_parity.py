@@ -260,7 +260,7 @@ def test_errors_do_not_cross_the_boundary(rtnw, ctx):
     import ctypes as C
     bad = rtnw.SceneDesc()
     C.memmove(C.byref(bad), C.byref(hs.desc), C.sizeof(bad))
-    bad.abi_version = 1
+    bad.abi_version = 3
     with pytest.raises(rtnw.RtnwError):
         ctx.upload(bad)
     ds.close()
@@ -304,4 +304,29 @@ def test_render_is_bitwise_deterministic(rtnw, ctx, name):
     for _ in range(2):
         b, sb = ds.render(cam, hs.params(nx=nx, ny=ny, ns=6, seed=77))
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and sa.rays == sb.rays
+    ds.close()
+
+
+def test_pixel_subset_and_accumulate(rtnw, ctx):
+    """rtnw_render_params.pixel_begin/stride/count + RTNW_F_ACCUMULATE (the multi-GPU split of left-over samples): rendering
+    7 samples as 3 (all pixels) + 4 (two interleaved pixel subsets, accumulated) reproduces the one-shot render."""
+    import torch
+    hs = rtnw.HostScene("cornell_box")
+    ds = ctx.upload(hs.desc_ptr)
+    nx = ny = 48
+    cam = hs.camera(nx, ny)
+    full, _ = ds.render(cam, hs.params(nx=nx, ny=ny, ns=7, seed=21))
+    acc = torch.full((ny, nx, 3), 123.0, dtype=torch.float32, device="cuda")
+    st = ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=3, seed=21), acc.data_ptr())
+    assert st.paths == nx * ny * 3
+    for r in range(2):
+        cnt = len(range(r, nx * ny, 2))
+        st = ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=4, seed=21, sample_begin=3, pixel_begin=r, pixel_stride=2, pixel_count=cnt,
+                                             flags_extra=rtnw.F_ACCUMULATE), acc.data_ptr())
+        assert st.paths == cnt * 4
+    assert np.allclose(acc.cpu().numpy(), full, rtol=1e-6, atol=1e-6)
+    with pytest.raises(rtnw.RtnwError):  # subsets are a device-buffer feature
+        ds.render(cam, hs.params(nx=nx, ny=ny, ns=1, pixel_begin=0, pixel_stride=2, pixel_count=10))
+    with pytest.raises(rtnw.RtnwError):
+        ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=1, pixel_begin=5, pixel_stride=1, pixel_count=nx * ny), acc.data_ptr())
     ds.close()

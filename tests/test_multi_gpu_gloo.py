@@ -35,9 +35,11 @@ def _worker(rank, world, port, ns, out_path):
     cam = hs.camera(nx, ny)
     accum = torch.zeros(ny, nx, 3, dtype=torch.float32)
 
-    def render(begin, count, stride):
-        sums, _ = op.render(rtnw, hs.desc_ptr, cam, hs.params(nx=nx, ny=ny, ns=count, seed=17, sample_begin=begin, sample_stride=stride))
-        accum.copy_(torch.from_numpy(sums))
+    def render(**launch):
+        p = hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=17, sample_begin=launch["sample_begin"],
+                      sample_stride=launch["sample_stride"], pixel_begin=launch["pixel_begin"], pixel_stride=launch["pixel_stride"],
+                      pixel_count=launch["pixel_count"], flags_extra=rtnw.F_ACCUMULATE if launch["accumulate"] else 0)
+        op.render(rtnw, hs.desc_ptr, cam, p, out=accum.numpy())  # the C oracle stands in for the kernel; same parameters
 
     mg.render_partitioned(render, accum, ns, dist=dist, dst=0)
     if rank == 0:
@@ -45,7 +47,7 @@ def _worker(rank, world, port, ns, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ns", [6, 1])
+@pytest.mark.parametrize("ns", [6, 1, 5])
 def test_two_ranks_partition_and_reduce(rtnw, tmp_path, ns):
     import torch.multiprocessing as mp
     import oracle_port as op
@@ -58,14 +60,24 @@ def test_two_ranks_partition_and_reduce(rtnw, tmp_path, ns):
     assert got.sum() > 0
 
 
-def test_sample_partition_covers_every_sample_once():
+def test_partition_plan_covers_every_path_exactly_once_and_evenly():
     mg = importlib.import_module("peter-shirley-ray-tracing-the-next-week_b200.multi_gpu")
+    npix = 37
     for ns in (0, 1, 7, 100):
         for world in (1, 2, 3, 8):
-            seen = []
+            seen = {}
+            work = []
             for r in range(world):
-                b, c, s = mg.sample_partition(ns, world, r)
-                seen += [b + k * s for k in range(c)]
-            assert sorted(seen) == list(range(ns))
+                w = 0
+                for l in mg.partition_plan(ns, npix, world, r):
+                    pixels = range(npix) if l["pixel_count"] == 0 else [l["pixel_begin"] + k * l["pixel_stride"] for k in range(l["pixel_count"])]
+                    for p in pixels:
+                        for k in range(l["sample_count"]):
+                            key = (p, l["sample_begin"] + k * l["sample_stride"])
+                            seen[key] = seen.get(key, 0) + 1
+                            w += 1
+                work.append(w)
+            assert len(seen) == npix * ns and set(seen.values()) <= {1}
+            assert max(work) - min(work) <= ns % world  # even up to one pixel's left-over samples
     with pytest.raises(ValueError):
-        mg.sample_partition(4, 2, 2)
+        mg.partition_plan(4, 10, 2, 2)
