@@ -180,14 +180,13 @@ def main():
     ds = ctx.upload(hs.desc_ptr)
     nx, ny, ns = WORKLOAD["nx"], WORKLOAD["ny"], WORKLOAD["ns"]
     cam = hs.camera(nx, ny)
-    plan = mg.partition_plan(ns, nx * ny, world, rank)  # evenly divisible samples by sample index, the rest by pixel
+    plan = mg.partition_plan(ns, nx * ny, world, rank)  # one launch; even for any ns (RTNW_F_ROTATE_SAMPLES)
 
-    def launch_params(launch, first):
-        extra = args.flags | (rtnw.F_ACCUMULATE if (launch["accumulate"] or not first) else 0)
+    def launch_params(launch):
+        extra = args.flags | (rtnw.F_ROTATE_SAMPLES if launch["rotate"] else 0) | (rtnw.F_ACCUMULATE if launch["accumulate"] else 0)
         return hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=SEED, sample_begin=launch["sample_begin"],
-                         sample_stride=launch["sample_stride"], flags_extra=extra, pixel_begin=launch["pixel_begin"],
-                         pixel_stride=launch["pixel_stride"], pixel_count=launch["pixel_count"])
-    params = launch_params(plan[0], True)  # world == 1: the whole frame in one launch
+                         sample_stride=launch["sample_stride"], flags_extra=extra)
+    params = launch_params(plan[0])  # world == 1: the whole frame in one launch
     accum = torch.empty(ny, nx, 3, dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
@@ -203,11 +202,7 @@ def main():
         last["rays"], last["kernel_ms"], last["launches"] = 0, 0.0, 0
 
         def render(**launch):
-            extra = args.flags | (rtnw.F_ACCUMULATE if launch["accumulate"] else 0)
-            p = hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=SEED, sample_begin=launch["sample_begin"],
-                          sample_stride=launch["sample_stride"], flags_extra=extra, pixel_begin=launch["pixel_begin"],
-                          pixel_stride=launch["pixel_stride"], pixel_count=launch["pixel_count"])
-            st = ds.render_device(cam, p, accum.data_ptr(), stream.cuda_stream)
+            st = ds.render_device(cam, launch_params(launch), accum.data_ptr(), stream.cuda_stream)
             last["rays"] += st.rays; last["kernel_ms"] += st.kernel_ms; last["launches"] += 1
         mg.render_partitioned(render, accum, ns, dist=dist, dst=0)  # k_render launches of this rank, then one NCCL reduce(sum)
         return last
@@ -260,11 +255,7 @@ def main():
             tot = {"ms": 0.0}
 
             def render2(**launch):
-                extra = args.flags | (rtnw.F_ACCUMULATE if launch["accumulate"] else 0)
-                p = hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=SEED, sample_begin=launch["sample_begin"],
-                              sample_stride=launch["sample_stride"], flags_extra=extra, pixel_begin=launch["pixel_begin"],
-                              pixel_stride=launch["pixel_stride"], pixel_count=launch["pixel_count"])
-                tot["ms"] += s2.render_device(cam, p, accum.data_ptr(), stream.cuda_stream).kernel_ms
+                tot["ms"] += s2.render_device(cam, launch_params(launch), accum.data_ptr(), stream.cuda_stream).kernel_ms
             mg.render_partitioned(render2, accum, ns, dist=dist, dst=0)
             e2e_kernel_ms.append(tot["ms"])
             if rank == 0:
@@ -322,7 +313,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "final_northstar 1000x1000x100spp (config 5N: BVH over 1024 floor boxes + "
                                    "translate(rotate_y(BVH over 1000 spheres)) + media + perlin + image texture)",
-                       "paths_per_step": paths_per_step, "partition": f"spp split over {world} GPU(s) (left-over samples by interleaved pixels), 1 NCCL reduce",
+                       "paths_per_step": paths_per_step, "partition": f"spp split over {world} GPU(s) (sample ownership rotates with the pixel index), 1 NCCL reduce",
                        "l2": "flushed between timed steps (256 MiB write)", "traversal": "narrowed" if args.flags & 4 else "reference-exact",
                        "seed": SEED},
             "mrays_per_s": mrays, "rays_per_path": tot_rays.item() / (paths_per_step * args.steps),

@@ -157,6 +157,10 @@ enum rtnw_background { RTNW_BG_BLACK = 0 /* PSC/main.cpp:44 */, RTNW_BG_SKY = 1 
                                     and leaves the reference's un-narrowed bvh_node::hit tests */
 #define RTNW_F_COUNTERS      8u  /* fill the optional work counters in rtnw_stats */
 #define RTNW_F_ACCUMULATE   16u  /* add this call's pixel sums to accum_rgb instead of overwriting (rtnw_render_device only) */
+#define RTNW_F_ROTATE_SAMPLES 32u /* multi-GPU split that is even for any ns: sample_count is the TOTAL number of samples ns of
+                                    the frame, and for pixel p this call renders the samples s in [0, ns) with
+                                    s = (sample_begin - p) mod sample_stride, + k*sample_stride: rank g of G passes
+                                    sample_begin = g, sample_stride = G; each pixel gets floor or ceil(ns/G) samples per rank */
 
 typedef struct rtnw_render_params {
     int32_t nx, ny;

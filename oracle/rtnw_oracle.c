@@ -620,6 +620,7 @@ int rtnw_oracle_render(const rtnw_scene_desc* d, const rtnw_camera* cam, const r
     stream_init(&g, P->seed);
     ctx c = {d, &g};
     struct timespec t0, t1;
+    uint64_t paths = 0;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int j = P->ny - 1; j >= 0; j--) {
         for (int i = 0; i < P->nx; i++) {
@@ -628,8 +629,15 @@ int rtnw_oracle_render(const rtnw_scene_desc* d, const rtnw_camera* cam, const r
                 if (rel < 0 || rel % P->pixel_stride != 0 || rel / P->pixel_stride >= P->pixel_count) continue;
             }
             vec3 col = V(0, 0, 0);
-            for (int k = 0; k < P->sample_count; k++) {
-                const int s = P->sample_begin + k * P->sample_stride;
+            int s_begin = P->sample_begin, s_count = P->sample_count;
+            if (P->flags & RTNW_F_ROTATE_SAMPLES) { /* samples (begin - p) mod G + k*G below ns = sample_count */
+                const int g_ = P->sample_stride, pix = j * P->nx + i;
+                s_begin = ((P->sample_begin - pix) % g_ + g_) % g_;
+                s_count = s_begin < P->sample_count ? (P->sample_count - s_begin + g_ - 1) / g_ : 0;
+            }
+            paths += (uint64_t)s_count;
+            for (int k = 0; k < s_count; k++) {
+                const int s = s_begin + k * P->sample_stride;
                 begin_path(&g, (uint32_t)(j * P->nx + i), (uint32_t)s);
                 ray r = camera_ray(cam, P->nx, P->ny, i, j, &g);
                 vec3 temp = color(&c, &r, 0, P);
@@ -646,7 +654,7 @@ int rtnw_oracle_render(const rtnw_scene_desc* d, const rtnw_camera* cam, const r
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (stats) {
-        stats[0] = (double)(P->pixel_count > 0 ? P->pixel_count : P->nx * P->ny) * P->sample_count;
+        stats[0] = (double)paths;
         stats[1] = (double)g.rays;
         stats[2] = (double)g.box_tests;
         stats[3] = (double)g.prim_tests;

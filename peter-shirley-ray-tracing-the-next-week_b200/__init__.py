@@ -25,7 +25,7 @@ RTNW_ABI_VERSION = 4
 RTNW_OK = 0
 RTNW_ERR_INVALID, RTNW_ERR_CUDA, RTNW_ERR_UNSUPPORTED, RTNW_ERR_NOMEM = -1, -2, -3, -4
 BG_BLACK, BG_SKY = 0, 1
-F_DE_NAN, F_EMIT, F_CULL_NARROW, F_COUNTERS, F_ACCUMULATE = 1, 2, 4, 8, 16
+F_DE_NAN, F_EMIT, F_CULL_NARROW, F_COUNTERS, F_ACCUMULATE, F_ROTATE_SAMPLES = 1, 2, 4, 8, 16, 32
 FLT_MAX = float(np.finfo(np.float32).max)
 
 

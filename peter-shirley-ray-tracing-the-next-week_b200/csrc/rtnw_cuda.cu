@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     const int nx = P.p.nx, ny = P.p.ny;
     const unsigned long long npix = (unsigned long long)P.p.pixel_count;  // render_core fills in the default subset
     const bool accumulate = (P.p.flags & RTNW_F_ACCUMULATE) != 0;
+    const bool rotate = (P.p.flags & RTNW_F_ROTATE_SAMPLES) != 0;
     const uint32_t k0 = (uint32_t)P.p.seed, k1 = (uint32_t)(P.p.seed >> 32);
     const bool emit = (P.p.flags & RTNW_F_EMIT) != 0;
     const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     if (threadIdx.x == 0) sm.overflow = 0;
     bool alive = true, need = true;
     int pix = -1, k = 0, depth = 0;
+    int s_begin = P.p.sample_begin, s_count = P.p.sample_count;  // the samples of the current pixel
     f3 col = mk3(0.f, 0.f, 0.f), L = col, T = col;
     ray_t wr;
     wr.o = col; wr.d = mk3(1.f, 1.f, 1.f); wr.time = 0.f;
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 
     for (;;) {
         // ---- next sample of the pixel, or next pixel, PSC/main.cpp:299-308
-        if (alive && need && pix >= 0 && k == P.p.sample_count) {
+        if (alive && need && pix >= 0 && k == s_count) {
             float* dst = P.accum + 3ull * (unsigned long long)pix;
             if (accumulate) { dst[0] += col.x; dst[1] += col.y; dst[2] += col.z; }
             else { dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; }
@@ -90,12 +92,19 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             if (want) {
                 const unsigned long long mine = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
                 if (mine >= npix) alive = false;
-                else { pix = P.p.pixel_begin + (int)mine * P.p.pixel_stride; k = 0; col = mk3(0.f, 0.f, 0.f); }
+                else {
+                    pix = P.p.pixel_begin + (int)mine * P.p.pixel_stride; k = 0; col = mk3(0.f, 0.f, 0.f);
+                    if (rotate) {  // RTNW_F_ROTATE_SAMPLES: ownership of the samples rotates with the pixel index
+                        const int g = P.p.sample_stride;
+                        s_begin = ((P.p.sample_begin - pix) % g + g) % g;
+                        s_count = s_begin < P.p.sample_count ? (P.p.sample_count - s_begin + g - 1) / g : 0;
+                    }
+                }
             }
         }
         if (__syncthreads_count(alive) == 0) break;
-        if (alive && need) {
-            const int s = P.p.sample_begin + k * P.p.sample_stride;
+        if (alive && need && k < s_count) {
+            const int s = s_begin + k * P.p.sample_stride;
             ++k;
             g.begin(k0, k1, (uint32_t)pix, (uint32_t)s);
             camera_ray(P.cam, nx, ny, pix % nx, pix / nx, g, wr);
@@ -107,9 +116,10 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
         // ---- world->hit(r, t_min, t_max, rec), PSC/main.cpp:27
         medium_key mk;
         mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)pix; mk.sample = g.sample; mk.depth = (uint32_t)depth;
-        const hkey_t key = coop_closest_hit<RTNW_BLOCK, COUNT>(P.S, sm, wr, alive, P.p.t_min, P.p.t_max, mk, cnt);
+        const bool tracing = alive && !need;  // a pixel that owns no sample of this call has no ray (RTNW_F_ROTATE_SAMPLES, ns < G)
+        const hkey_t key = coop_closest_hit<RTNW_BLOCK, COUNT>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt);
         // ---- one level of color(), PSC/main.cpp:25-46, in iterative form
-        if (alive) {
+        if (tracing) {
             ++n_rays;
             hit_t h;
             key_to_hit(P.S, key, P.p.t_max, h);
@@ -693,7 +703,20 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     if (h[4]) return fail(RTNW_ERR_UNSUPPORTED, "BVH task stack overflow: the tree is deeper than RTNW_QN/RTNW_BLOCK - 1 levels");
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
-        stats->paths = (uint64_t)a.p.pixel_count * p->sample_count;
+        if (p->flags & RTNW_F_ROTATE_SAMPLES) {  // per pixel: the samples s = (begin - p) mod G + k*G below ns
+            uint64_t paths = 0;
+            const int g = p->sample_stride;
+            for (int r = 0; r < g; ++r) {  // pixels whose index is r mod G
+                const int b = ((p->sample_begin - r) % g + g) % g;
+                const uint64_t per_pixel = b < p->sample_count ? (uint64_t)(p->sample_count - b + g - 1) / g : 0;
+                uint64_t n_pix = 0;
+                for (long long k = 0; k < a.p.pixel_count; ++k) n_pix += ((a.p.pixel_begin + k * a.p.pixel_stride) % g) == r;
+                paths += per_pixel * n_pix;
+            }
+            stats->paths = paths;
+        } else {
+            stats->paths = (uint64_t)a.p.pixel_count * p->sample_count;
+        }
         stats->rays = h[1];
         stats->box_tests = h[2];
         stats->prim_tests = h[3];

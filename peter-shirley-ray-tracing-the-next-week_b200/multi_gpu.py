@@ -15,24 +15,26 @@ def sample_partition(ns: int, world: int, rank: int) -> tuple[int, int, int]:
 
 
 def partition_plan(ns: int, npix: int, world: int, rank: int) -> list[dict]:
-    """The launches of `rank` so that every rank does ns/world samples' worth of work for ANY ns:
-      1. the samples that divide evenly, split by sample index: rank, rank+world, ... below world*(ns//world);
-      2. the ns % world left-over samples, split by interleaved PIXELS: pixel p is done by rank p % world, added into the
-         same buffer (RTNW_F_ACCUMULATE).
-    Each dict holds keyword overrides for the render parameters; `accumulate` is True for launches after the first."""
+    """The launches of `rank` (keyword overrides for the render parameters).  One launch: with RTNW_F_ROTATE_SAMPLES the
+    ownership of the samples rotates with the pixel index — rank g renders, for pixel p, the samples s in [0, ns) with
+    s = (g - p) mod world (+ k*world) — so every rank traces floor or ceil(ns/world) samples of every pixel and the
+    remainder ns % world is spread evenly over the pixels: per-rank work is even for ANY ns, in a single kernel launch.
+    (For world == 1 this is the plain render.)"""
     if not (0 <= rank < world) or ns < 0 or npix < 0:
         raise ValueError("bad partition arguments")
-    base, rem = divmod(ns, world)
-    plan = []
-    if base > 0:
-        plan.append(dict(sample_begin=rank, sample_count=base, sample_stride=world, pixel_begin=0, pixel_stride=1, pixel_count=0,
-                         accumulate=False))
-    if rem > 0:
-        count = len(range(rank, npix, world))
-        if count > 0:
-            plan.append(dict(sample_begin=base * world, sample_count=rem, sample_stride=1, pixel_begin=rank, pixel_stride=world,
-                             pixel_count=count, accumulate=bool(plan)))
-    return plan
+    if ns == 0 or npix == 0:
+        return []
+    if world == 1:
+        return [dict(sample_begin=0, sample_count=ns, sample_stride=1, rotate=False, accumulate=False)]
+    return [dict(sample_begin=rank, sample_count=ns, sample_stride=world, rotate=True, accumulate=False)]
+
+
+def samples_of(launch: dict, pixel: int) -> list[int]:
+    """the sample indices a launch of partition_plan() renders for `pixel` (what the kernel computes per pixel)"""
+    g = launch["sample_stride"]
+    if not launch["rotate"]:
+        return [launch["sample_begin"] + k * g for k in range(launch["sample_count"])]
+    return list(range((launch["sample_begin"] - pixel) % g, launch["sample_count"], g))
 
 
 def render_partitioned(render_fn, accum, ns: int, dist=None, dst: int = 0, npix: int | None = None):
@@ -44,10 +46,8 @@ def render_partitioned(render_fn, accum, ns: int, dist=None, dst: int = 0, npix:
     if npix is None:
         npix = accum.numel() // 3
     plan = partition_plan(ns, npix, world, rank)
-    if not plan or plan[0]["pixel_count"] != 0:
-        accum.zero_()  # nothing rendered, or only a pixel subset: the rest of the buffer must be zero
-        for launch in plan:
-            launch["accumulate"] = True
+    if not plan:
+        accum.zero_()
     for launch in plan:
         render_fn(**launch)
     if dist is not None and world > 1:

@@ -330,3 +330,28 @@ def test_pixel_subset_and_accumulate(rtnw, ctx):
     with pytest.raises(rtnw.RtnwError):
         ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=1, pixel_begin=5, pixel_stride=1, pixel_count=nx * ny), acc.data_ptr())
     ds.close()
+
+
+@pytest.mark.parametrize("ns,world", [(7, 3), (10, 8), (3, 8), (12, 4)])
+def test_rotated_sample_split_is_an_even_partition(rtnw, ctx, ns, world):
+    """RTNW_F_ROTATE_SAMPLES (the multi-GPU split): the ranks' renders sum to the single render for any ns, including
+    ns < world (pixels that own no sample on a rank), and every rank traces the same number of paths +- npix % world."""
+    import oracle_port as op
+    hs = rtnw.HostScene("cornell_box")
+    ds = ctx.upload(hs.desc_ptr)
+    nx, ny = 40, 30
+    cam = hs.camera(nx, ny)
+    full, _ = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=33))
+    total = np.zeros_like(full, dtype=np.float64)
+    paths = []
+    for g in range(world):
+        p = hs.params(nx=nx, ny=ny, ns=ns, seed=33, sample_begin=g, sample_stride=world, flags_extra=rtnw.F_ROTATE_SAMPLES)
+        part, st = ds.render(cam, p)
+        ref, ost = op.render(rtnw, hs.desc_ptr, cam, p)
+        assert st.paths == ost["paths"]
+        assert np.isclose(part, ref, rtol=2e-5, atol=1e-6).all(axis=2).mean() >= 0.99
+        total += part
+        paths.append(st.paths)
+    assert sum(paths) == nx * ny * ns and max(paths) - min(paths) <= nx * ny % world + world
+    assert np.allclose(total, full, rtol=1e-5, atol=1e-6)
+    ds.close()

@@ -37,8 +37,7 @@ def _worker(rank, world, port, ns, out_path):
 
     def render(**launch):
         p = hs.params(nx=nx, ny=ny, ns=launch["sample_count"], seed=17, sample_begin=launch["sample_begin"],
-                      sample_stride=launch["sample_stride"], pixel_begin=launch["pixel_begin"], pixel_stride=launch["pixel_stride"],
-                      pixel_count=launch["pixel_count"], flags_extra=rtnw.F_ACCUMULATE if launch["accumulate"] else 0)
+                      sample_stride=launch["sample_stride"], flags_extra=rtnw.F_ROTATE_SAMPLES if launch["rotate"] else 0)
         op.render(rtnw, hs.desc_ptr, cam, p, out=accum.numpy())  # the C oracle stands in for the kernel; same parameters
 
     mg.render_partitioned(render, accum, ns, dist=dist, dst=0)
@@ -70,14 +69,12 @@ def test_partition_plan_covers_every_path_exactly_once_and_evenly():
             for r in range(world):
                 w = 0
                 for l in mg.partition_plan(ns, npix, world, r):
-                    pixels = range(npix) if l["pixel_count"] == 0 else [l["pixel_begin"] + k * l["pixel_stride"] for k in range(l["pixel_count"])]
-                    for p in pixels:
-                        for k in range(l["sample_count"]):
-                            key = (p, l["sample_begin"] + k * l["sample_stride"])
-                            seen[key] = seen.get(key, 0) + 1
+                    for p in range(npix):
+                        for smp in mg.samples_of(l, p):
+                            seen[(p, smp)] = seen.get((p, smp), 0) + 1
                             w += 1
                 work.append(w)
             assert len(seen) == npix * ns and set(seen.values()) <= {1}
-            assert max(work) - min(work) <= ns % world  # even up to one pixel's left-over samples
+            assert max(work) - min(work) <= max(1, npix % world)  # even: at most a few paths apart
     with pytest.raises(ValueError):
         mg.partition_plan(4, 10, 2, 2)
