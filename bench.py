@@ -233,6 +233,14 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot_rays, op=dist.ReduceOp.SUM)
     total_s = total_ms.item() / 1e3
+    # per-rank kernel time and step time (diagnoses a slow GPU / a slow reduce when the max over ranks is off)
+    mine = torch.tensor([sum(kernel_ms) / len(kernel_ms), sum(step_ms) / len(step_ms)], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = [[round(float(x), 3) for x in t.tolist()] for t in per_rank]
     paths_per_step = nx * ny * ns
     value = paths_per_step * args.steps / total_s / 1e6
     mrays = tot_rays.item() / total_s / 1e6
@@ -321,6 +329,7 @@ def main():
                     "d2h_bytes_per_step": nx * ny * 3 * 4, "ms_per_step": 1e3 * e2e_s.item() / args.steps,
                     "kernel_ms_per_step": sum(e2e_kernel_ms[-args.steps:]) / args.steps},
             "gpu_launches": args.steps * launches_per_step,
+            "per_rank_ms": {"kernel": [r[0] for r in per_rank], "step": [r[1] for r in per_rank]},
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch, ncu --set full capture

@@ -706,11 +706,17 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
         if (p->flags & RTNW_F_ROTATE_SAMPLES) {  // per pixel: the samples s = (begin - p) mod G + k*G below ns
             uint64_t paths = 0;
             const int g = p->sample_stride;
+            auto floordiv = [](long long x, long long y) { return x >= 0 ? x / y : -((-x + y - 1) / y); };
             for (int r = 0; r < g; ++r) {  // pixels whose index is r mod G
                 const int b = ((p->sample_begin - r) % g + g) % g;
                 const uint64_t per_pixel = b < p->sample_count ? (uint64_t)(p->sample_count - b + g - 1) / g : 0;
                 uint64_t n_pix = 0;
-                for (long long k = 0; k < a.p.pixel_count; ++k) n_pix += ((a.p.pixel_begin + k * a.p.pixel_stride) % g) == r;
+                if (a.p.pixel_stride == 1) {  // integers in [begin, begin+count) congruent to r
+                    const long long lo = a.p.pixel_begin, hi = (long long)a.p.pixel_begin + a.p.pixel_count - 1;
+                    n_pix = (uint64_t)(floordiv(hi - r, g) - floordiv(lo - 1 - r, g));
+                } else {
+                    for (long long k = 0; k < a.p.pixel_count; ++k) n_pix += ((a.p.pixel_begin + k * a.p.pixel_stride) % g) == r;
+                }
                 paths += per_pixel * n_pix;
             }
             stats->paths = paths;
