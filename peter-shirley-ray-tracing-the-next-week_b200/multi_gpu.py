@@ -7,13 +7,6 @@ step on this path, hence no other collective.
 from __future__ import annotations
 
 
-def sample_partition(ns: int, world: int, rank: int) -> tuple[int, int, int]:
-    """(sample_begin, sample_count, sample_stride) of `rank`: samples rank, rank+world, ... below ns."""
-    if not (0 <= rank < world) or ns < 0:
-        raise ValueError("bad partition arguments")
-    return rank, len(range(rank, ns, world)), world
-
-
 def partition_plan(ns: int, npix: int, world: int, rank: int) -> list[dict]:
     """The launches of `rank` (keyword overrides for the render parameters).  One launch: with RTNW_F_ROTATE_SAMPLES the
     ownership of the samples rotates with the pixel index — rank g renders, for pixel p, the samples s in [0, ns) with
