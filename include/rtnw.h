@@ -238,6 +238,13 @@ int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
 int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam,
                        const rtnw_render_params* params, float* accum_rgb_dev, void* cuda_stream, rtnw_stats* stats);
 
+/* Output stage on the device, PSC/main.cpp:315-325: col = sums/ns (vec3::operator/=: multiply by float(1.0/ns)), sqrt gamma,
+ * int(255.99*c) in double, optional clamp to 255.  accum_rgb_dev = nx*ny*3 float sums in DEVICE memory (e.g. the buffer
+ * rtnw_render_device filled and NCCL reduced); rgb_out = nx*ny*3 int32 in HOST memory, in the reference's output order
+ * (top row first).  Identical to rtnw_host_quantize on the same sums. */
+int rtnw_quantize_device(rtnw_ctx* ctx, const float* accum_rgb_dev, int32_t nx, int32_t ny, int32_t ns, int32_t clamp255,
+                         int32_t* rgb_out);
+
 /* Deterministic closest-hit query: one `world->hit(r, t_min, t_max, rec)` per ray (PSC/main.cpp:27).  Host buffers.
  * flags: reserved.  Media draw their free-flight number from Philox(seed; medium leaf id, depth 0, sample 0, pixel = ray.key),
  * so results do not depend on traversal order. */

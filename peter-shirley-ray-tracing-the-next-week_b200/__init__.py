@@ -111,7 +111,7 @@ assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 48
 
 # every symbol include/rtnw.h and include/rtnw_host.h declare (tests check the libraries export all of them)
 DEVICE_SYMBOLS = ["rtnw_last_error", "rtnw_abi_version", "rtnw_device_count", "rtnw_ctx_create", "rtnw_ctx_destroy",
-                  "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
+                  "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_quantize_device", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
                   "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays"]
 HOST_SYMBOLS = ["rtnw_host_last_error", "rtnw_host_scene_build", "rtnw_host_scene_free", "rtnw_host_scene_desc",
                 "rtnw_host_scene_leaf_count", "rtnw_host_scene_camera", "rtnw_host_scene_view", "rtnw_host_make_camera",
@@ -166,6 +166,7 @@ def device_lib() -> C.CDLL:
         L.rtnw_ctx_destroy.argtypes = [C.c_void_p]
         L.rtnw_ctx_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
         L.rtnw_measure_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.rtnw_quantize_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.rtnw_scene_upload.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
         L.rtnw_scene_free.argtypes = [C.c_void_p, C.c_void_p]
         L.rtnw_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]
@@ -276,6 +277,12 @@ class Context:
         v = C.c_float()
         _check_dev(device_lib().rtnw_measure_fp32_peak(self._h, C.byref(v)))
         return float(v.value)
+
+    def quantize_device(self, dev_ptr: int, nx: int, ny: int, ns: int, clamp255: bool = True) -> np.ndarray:
+        """PSC/main.cpp:315-325 on the GPU from a device buffer of sums; returns (ny, nx, 3) int32, top row first."""
+        out = np.empty((ny, nx, 3), dtype=np.int32)
+        _check_dev(device_lib().rtnw_quantize_device(self._h, C.c_void_p(dev_ptr), nx, ny, ns, int(clamp255), out.ctypes.data))
+        return out
 
     def upload(self, desc) -> "DeviceScene":
         return DeviceScene(self, desc)

@@ -217,6 +217,21 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     out[q] = o;
 }
 
+// the epilogue of the sample loop, PSC/main.cpp:315-325, one thread per pixel; output row 0 = top row (j = ny-1)
+__global__ void k_quantize(const float* __restrict__ sums, int nx, int ny, float inv_ns, int clamp255, int32_t* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nx * ny) return;
+    const int row = q / nx, i = q - row * nx, j = ny - 1 - row;
+    const float* src = sums + 3ull * ((unsigned long long)j * nx + i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float col = sqrtf(src[c] * inv_ns);      // col /= float(ns) multiplies by k = float(1.0/ns), PSC/vec3.h:134-141
+        int v = (int)(255.99 * (double)col);            // int(255.99*col[c]): the product is a double
+        if (clamp255 && v > 255) v = 255;
+        out[3ull * q + c] = v;
+    }
+}
+
 // FP32 issue peak of the device, measured: 8 independent FFMA chains per thread (the roofline denominator of bench.py)
 __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -974,6 +989,21 @@ int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
     return rc;
+}
+
+int rtnw_quantize_device(rtnw_ctx* ctx, const float* accum_rgb_dev, int32_t nx, int32_t ny, int32_t ns, int32_t clamp255, int32_t* rgb_out) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!accum_rgb_dev || !rgb_out || nx <= 0 || ny <= 0 || ns <= 0) return fail(RTNW_ERR_INVALID, "bad quantize arguments");
+    const size_t n = (size_t)nx * ny;
+    dev_buf d_out;
+    CUDA_TRY(d_out.alloc(n * 3 * sizeof(int32_t)));
+    const float inv_ns = (float)(1.0 / (double)(float)ns);
+    k_quantize<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(accum_rgb_dev, nx, ny, inv_ns, clamp255, d_out.as<int32_t>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, d_out.p, n * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
 }
 
 int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, size_t n, float t_min, float t_max, uint32_t flags,

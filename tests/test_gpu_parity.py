@@ -355,3 +355,23 @@ def test_rotated_sample_split_is_an_even_partition(rtnw, ctx, ns, world):
     assert sum(paths) == nx * ny * ns and max(paths) - min(paths) <= nx * ny % world + world
     assert np.allclose(total, full, rtol=1e-5, atol=1e-6)
     ds.close()
+
+
+def test_device_epilogue_equals_host_epilogue(rtnw, ctx):
+    """rtnw_quantize_device (gamma + quantise + clamp on the GPU, after the reduce) is bit-identical to the host epilogue
+    rtnw_host_quantize, which restates PSC/main.cpp:315-325; includes values > 1 (light), 0 and NaN-free negatives."""
+    import torch
+    hs = rtnw.HostScene("cornell_box")
+    ds = ctx.upload(hs.desc_ptr)
+    nx, ny, ns = 64, 48, 10
+    acc = torch.empty(ny, nx, 3, dtype=torch.float32, device="cuda")
+    ds.render_device(hs.camera(nx, ny), hs.params(nx=nx, ny=ny, ns=ns, seed=3), acc.data_ptr())
+    sums = acc.cpu().numpy()
+    for clamp in (True, False):
+        assert np.array_equal(ctx.quantize_device(acc.data_ptr(), nx, ny, ns, clamp), rtnw.quantize(sums, ns, clamp))
+    rng = np.random.default_rng(0)
+    synth = (rng.random((ny, nx, 3)) * rng.choice([0.0, 1.0, 50.0, 4000.0], (ny, nx, 1))).astype(np.float32)
+    t = torch.from_numpy(synth).cuda()
+    for n in (1, 3, 100, 1000):
+        assert np.array_equal(ctx.quantize_device(t.data_ptr(), nx, ny, n, True), rtnw.quantize(synth, n, True))
+    ds.close()
