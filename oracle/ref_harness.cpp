@@ -387,6 +387,8 @@ ref_scene* ref_scene_build(const char* name_c, int tagged_build) {
     else if (name == "simple_light") w = simple_light();
     else if (name == "two_spheres") w = two_spheres();
     else if (name == "earth") w = h_earth();
+    else if (name == "random_scene") w = random_scene();
+    else if (name == "test") w = test();
     else if (name == "final_northstar") { w = h_final_northstar(*S); pre_tagged = true; }
     else { delete S; return NULL; }
     hitable_list* flat = static_cast<hitable_list*>(w);

@@ -52,6 +52,8 @@ int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
     else if (name == "simple_light") { world = simple_light(); v = view_two_perlin(); v.sky = false; v.emit = true; }
     else if (name == "two_spheres") { world = two_spheres(); v = view_cornell(); v.sky = true; }
     else if (name == "earth") { world = earth(); v = view_cornell(); }
+    else if (name == "random_scene") { world = random_scene(); v = view_ch01(); v.emit = true; }
+    else if (name == "test") { world = test_scene(); v = view_two_perlin(); v.sky = false; v.emit = true; }
     else if (name == "stress_shells") { world = stress_shells(); v = view_ch01(); v.aperture = 0.0f; }
     else return fail(RTNW_ERR_INVALID, "unknown scene name: " + name);
     if (wrap) world = wrap_in_bvh(world, 0, 1);

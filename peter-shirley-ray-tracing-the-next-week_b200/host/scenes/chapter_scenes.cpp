@@ -73,6 +73,48 @@ hitable* random_scene_ch01() {
     return w.as_list();
 }
 
+// PSC/main.cpp:48-85, the live version: checker ground, the diffuse branch commented out (it draws nothing), metal and
+// glass small spheres.  Draws spelled out in g++'s right-to-left argument order, as in random_scene_ch01().
+hitable* random_scene() {
+    pool w(501);
+    texture* checker = new checker_texture(new constant_texture(vec3(0.2, 0.3, 0.1)), new constant_texture(vec3(0.9, 0.9, 0.9)));
+    w.add(new sphere(vec3(0, -700, 0), 700, new lambertian(checker)));
+    for (int a = -11; a < 11; a++) {
+        for (int b = -11; b < 11; b++) {
+            const float choose_mat = drand48();
+            const double dz = drand48();
+            const double dx = drand48();
+            const vec3 center(a + 0.9 * dx, 0.2, b + 0.9 * dz);
+            if (!((center - vec3(4, 0.2, 0)).length() > 0.9)) continue;
+            if (choose_mat < 0.8) {
+                // diffuse: commented out in the reference
+            } else if (choose_mat < 0.95) {
+                const double fuzz = drand48();
+                const double cb = drand48();
+                const double cg = drand48();
+                const double cr = drand48();
+                w.add(new sphere(center, 0.2, new metal(vec3(0.5 * (1 + cr), 0.5 * (1 + cg), 0.5 * (1 + cb)), 0.5 * fuzz)));
+            } else {
+                w.add(new sphere(center, 0.2, new dielectric(1.5)));
+            }
+        }
+    }
+    w.add(new sphere(vec3(0, 1, 0), 1.0, new dielectric(2.5)));
+    w.add(new sphere(vec3(-4, 1, 0), 1.0, matte(0.4, 0.2, 0.1)));
+    w.add(new sphere(vec3(4, 1, 0), 1.0, new metal(vec3(1, 1, 1), 0.0)));
+    return w.as_list();
+}
+
+// PSC/main.cpp:135-145
+hitable* test_scene() {
+    texture* checker = new checker_texture(new constant_texture(vec3(0.2, 0.3, 0.1)), new constant_texture(vec3(0.9, 0.9, 0.9)));
+    pool w(3);
+    w.add(new sphere(vec3(0, -700, 0), 700, new lambertian(checker)));
+    w.add(new sphere(vec3(0, 2, 0), 2, new lambertian(new noise_texture(4))));
+    w.add(new sphere(vec3(0, 7, 0), 2, lamp(11)));
+    return w.as_list();
+}
+
 hitable* two_perlin_spheres() {
     texture* checker = new checker_texture(new constant_texture(vec3(0.2, 0.3, 0.1)), new constant_texture(vec3(0.9, 0.9, 0.9)));
     pool w(2);

@@ -27,6 +27,8 @@ hitable* cornell_smoke();          // config 4: PSC/main.cpp:169-188
 hitable* final_scene();            // config 5R: PSC/main.cpp:190-230 (flat list, nb = 10)
 hitable* final_northstar();        // config 5N: nb = 32 floor boxes in a bvh_node, 1000-sphere cluster in
                                    //            translate(rotate_y(bvh_node)), synthetic earth image texture
+hitable* random_scene();           // PSC/main.cpp:48-85 (live version: checker ground, metal + glass spheres)
+hitable* test_scene();             // PSC/main.cpp:135-145
 hitable* simple_light();           // PSC/main.cpp:122-133
 hitable* two_spheres();            // PSC/main.cpp:99-110
 hitable* earth();                  // PSC/main.cpp:87-97 with the synthetic RGB8 image

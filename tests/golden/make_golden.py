@@ -19,9 +19,9 @@ import ref_oracle as ro  # noqa: E402
 from raysets import FLT_MAX, make_rays  # noqa: E402
 
 TRACE = ["ch01_random", "two_perlin", "cornell_box", "cornell_smoke", "final", "final+bvh", "final_northstar", "earth",
-         "simple_light", "cornell_smoke+bvh"]
+         "simple_light", "cornell_smoke+bvh", "random_scene+bvh", "test"]
 RENDER = [("ch01_random", 32, 16, 4), ("two_perlin", 32, 16, 4), ("cornell_box", 24, 24, 6), ("cornell_smoke", 24, 24, 6),
-          ("final", 20, 20, 2), ("final+bvh", 24, 24, 3), ("final_northstar", 48, 48, 4), ("simple_light", 32, 16, 4), ("earth", 20, 20, 3)]
+          ("final", 20, 20, 2), ("final+bvh", 24, 24, 3), ("final_northstar", 48, 48, 4), ("simple_light", 32, 16, 4), ("earth", 20, 20, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4)]
 
 
 def fname(kind, scene):

@@ -63,6 +63,8 @@ VIEWS = {
     "cornell_smoke": dict(lookfrom=(278, 278, -800), lookat=(278, 278, 0), vfov=40, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=1),
     "earth": dict(lookfrom=(278, 278, -800), lookat=(278, 278, 0), vfov=40, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=1),
     "two_spheres": dict(lookfrom=(278, 278, -800), lookat=(278, 278, 0), vfov=40, aperture=0.0, t_min=0.001, sky=1, emit=1, denan=1),
+    "random_scene": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vfov=20, aperture=0.1, t_min=0.001, sky=1, emit=1, denan=0),
+    "test": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vfov=20, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=0),
     "final": dict(lookfrom=(228, 278, -800), lookat=(278, 278, 0), vfov=40, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=1),
     "final_northstar": dict(lookfrom=(228, 278, -800), lookat=(278, 278, 0), vfov=40, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=1),
 }

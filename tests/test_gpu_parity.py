@@ -14,7 +14,7 @@ from raysets import FLT_MAX, assert_hits_equal, make_rays
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ro.available(), reason="oracle/_ref/libref_oracle.so not built")]
 
 TRACE_SCENES = ["ch01_random", "two_perlin", "cornell_box", "cornell_smoke", "final", "final+bvh", "final_northstar", "earth",
-                "simple_light", "cornell_smoke+bvh"]
+                "simple_light", "cornell_smoke+bvh", "random_scene", "random_scene+bvh", "test"]
 
 
 @pytest.mark.parametrize("name", TRACE_SCENES)
@@ -169,7 +169,7 @@ def test_scatter_and_emitted_same_stream(rtnw, ctx, kind, rgb, f, scale):
 
 RENDER_CASES = [("ch01_random", 64, 32, 6), ("two_perlin", 64, 32, 6), ("cornell_box", 48, 48, 8), ("cornell_smoke", 48, 48, 8),
                 ("final", 40, 40, 4), ("final+bvh", 40, 40, 4), ("final_northstar", 40, 40, 4), ("simple_light", 48, 24, 6),
-                ("earth", 40, 40, 4)]
+                ("earth", 40, 40, 4), ("random_scene", 64, 32, 6), ("test", 48, 24, 6)]
 
 
 @pytest.mark.parametrize("name,nx,ny,ns", RENDER_CASES)

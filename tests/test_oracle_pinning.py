@@ -12,7 +12,7 @@ from raysets import FLT_MAX, assert_hits_equal, make_rays
 pytestmark = pytest.mark.skipif(not ro.available(), reason="oracle/_ref/libref_oracle.so not built (needs /root/reference)")
 
 SCENES = ["ch01_random", "two_perlin", "cornell_box", "cornell_smoke", "final", "final+bvh", "final_northstar", "earth",
-          "simple_light", "ch01_random+bvh", "cornell_box+bvh", "cornell_smoke+bvh"]
+          "simple_light", "random_scene", "test", "random_scene+bvh", "ch01_random+bvh", "cornell_box+bvh", "cornell_smoke+bvh"]
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -25,7 +25,7 @@ def test_port_closest_hit_bit_exact(rtnw, name):
 
 @pytest.mark.parametrize("name,nx,ny,ns", [("ch01_random", 48, 24, 4), ("two_perlin", 48, 24, 4), ("cornell_box", 32, 32, 6),
                                             ("cornell_smoke", 32, 32, 6), ("final", 24, 24, 2), ("final+bvh", 32, 32, 3),
-                                            ("final_northstar", 32, 32, 3), ("simple_light", 32, 16, 4), ("earth", 24, 24, 3)])
+                                            ("final_northstar", 32, 32, 3), ("simple_light", 32, 16, 4), ("earth", 24, 24, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4)])
 def test_port_render_bit_exact(rtnw, name, nx, ny, ns):
     hs = rtnw.HostScene(name)
     got, st = op.render(rtnw, hs.desc_ptr, hs.camera(nx, ny), hs.params(nx=nx, ny=ny, ns=ns, seed=99))

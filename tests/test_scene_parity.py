@@ -12,7 +12,7 @@ import ref_oracle as ro
 pytestmark = pytest.mark.skipif(not ro.available(), reason="oracle/_ref/libref_oracle.so not built")
 
 SCENES = ["ch01_random", "two_perlin", "cornell_box", "cornell_smoke", "final", "final+bvh", "final_northstar", "earth",
-          "simple_light", "two_spheres"]
+          "simple_light", "two_spheres", "random_scene", "test"]
 
 
 def _tables(rtnw, hs):
