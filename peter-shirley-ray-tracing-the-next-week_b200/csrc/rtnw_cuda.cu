@@ -23,6 +23,11 @@ using namespace rtnw_dev;
 #ifndef RTNW_MIN_BLOCKS
 #define RTNW_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for
 #endif
+#ifndef RTNW_GROUP
+#define RTNW_GROUP RTNW_BLOCK  // threads that traverse BVH items cooperatively: the whole block, or 32 = one warp
+#endif
+static_assert(RTNW_GROUP == RTNW_BLOCK || RTNW_GROUP == 32,
+              "cooperating group = the whole block (__syncthreads) or one warp (__syncwarp); other sizes would need named barriers");
 
 // ================================================================================================ kernels
 struct render_args {
@@ -33,7 +38,8 @@ struct render_args {
     unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests, [4] task stack overflows
 };
 
-typedef coop_smem<RTNW_BLOCK> block_smem;
+typedef coop_smem<RTNW_GROUP> group_smem;
+struct block_smem { group_smem g[RTNW_BLOCK / RTNW_GROUP]; };
 
 // The sample loop of PSC/main.cpp:299-313 as ONE persistent megakernel.
 //
@@ -49,7 +55,7 @@ typedef coop_smem<RTNW_BLOCK> block_smem;
 template <bool COUNT>
 __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const render_args P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    block_smem& sm = *reinterpret_cast<block_smem*>(smem_raw);
+    group_smem& sm = reinterpret_cast<block_smem*>(smem_raw)->g[threadIdx.x / RTNW_GROUP];
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int nx = P.p.nx, ny = P.p.ny;
@@ -61,7 +67,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
     const bool sky = P.p.background == RTNW_BG_SKY;
 
-    if (threadIdx.x == 0) sm.overflow = 0;
+    if (threadIdx.x % RTNW_GROUP == 0) sm.overflow = 0;
     bool alive = true, need = true;
     int pix = -1, k = 0, depth = 0;
     int s_begin = P.p.sample_begin, s_count = P.p.sample_count;  // the samples of the current pixel
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                 }
             }
         }
-        if (__syncthreads_count(alive) == 0) break;
+        if (RTNW_GROUP == 32 ? __ballot_sync(FULL, alive) == 0 : __syncthreads_count(alive) == 0) break;  // the group is done
         if (alive && need && k < s_count) {
             const int s = s_begin + k * P.p.sample_stride;
             ++k;
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
         medium_key mk;
         mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)pix; mk.sample = g.sample; mk.depth = (uint32_t)depth;
         const bool tracing = alive && !need;  // a pixel that owns no sample of this call has no ray (RTNW_F_ROTATE_SAMPLES, ns < G)
-        const hkey_t key = coop_closest_hit<RTNW_BLOCK, COUNT>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt);
+        const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt);
         // ---- one level of color(), PSC/main.cpp:25-46, in iterative form
         if (tracing) {
             ++n_rays;
@@ -161,7 +167,8 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             }
         }
     }
-    if (threadIdx.x == 0 && sm.overflow) atomicAdd(&P.ctr[4], 1ull);
+    group_sync<RTNW_GROUP>();
+    if (threadIdx.x % RTNW_GROUP == 0 && sm.overflow) atomicAdd(&P.ctr[4], 1ull);
     // work counters: one atomic per warp
     if (COUNT) { box_total = cnt.box_tests; prim_total = cnt.prim_tests; }
     for (int o = 16; o > 0; o >>= 1) n_rays += __shfl_xor_sync(FULL, n_rays, o);
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const rtnw_ray* __restrict__ rays, size_t n, float t_min,
                                                       float t_max, uint64_t seed, rtnw_hit* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    block_smem& sm = *reinterpret_cast<block_smem*>(smem_raw);
+    group_smem& sm = reinterpret_cast<block_smem*>(smem_raw)->g[threadIdx.x / RTNW_GROUP];
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = q < n;  // idle threads of the last block still work on the block's BVH tasks
     rtnw_ray in;
@@ -194,8 +201,8 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     mk.k0 = (uint32_t)seed; mk.k1 = (uint32_t)(seed >> 32); mk.pixel = in.key; mk.sample = 0; mk.depth = 0;
     trav_counters cnt;
     cnt.box_tests = 0; cnt.prim_tests = 0;
-    if (threadIdx.x == 0) sm.overflow = 0;
-    const hkey_t key = coop_closest_hit<RTNW_BLOCK, false>(S, sm, r, active, t_min, t_max, mk, cnt);
+    if (threadIdx.x % RTNW_GROUP == 0) sm.overflow = 0;
+    const hkey_t key = coop_closest_hit<RTNW_GROUP, false>(S, sm, r, active, t_min, t_max, mk, cnt);
     if (!active) return;
     hit_t h;
     key_to_hit(S, key, t_max, h);
@@ -597,7 +604,7 @@ struct stream_builder {
         max_wide_depth = 0;
         root_out = emit_wide(bt, broot, 0);
         depth_out = max_wide_depth + 1;
-        if (RTNW_BLOCK + 3 * depth_out + 8 > RTNW_QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
+        if (RTNW_GROUP + 3 * depth_out + 8 > group_smem::QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
         return true;
     }
 

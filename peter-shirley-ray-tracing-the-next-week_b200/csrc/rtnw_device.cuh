@@ -414,25 +414,28 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, cons
 // leaving 3*depth slots in reserve: with take = 1 the traversal is a plain depth-first walk, which needs at most
 // 3*(depth - d) slots above a task at depth d.  Hence the stack cannot overflow for a tree of any depth, and the usual
 // case (room for everything) runs BLOCK tasks wide.
-#ifndef RTNW_QN
-#define RTNW_QN 6144  // node task stack
-#endif
-#ifndef RTNW_QL
-#define RTNW_QL 4096  // gate queue (circular, power of two); node work pauses while fewer than 4*BLOCK slots are free
-#endif
-template <int BLOCK>
+// The cooperating GROUP is a template parameter: a whole block (group_sync = __syncthreads) or a single warp
+// (group_sync = __syncwarp: no block barrier anywhere, every warp of the SM progresses independently; with 32 lanes the
+// round policy below degenerates to "node rounds until the stack is empty, then 32-wide gate rounds").
+template <int GROUP>
+__device__ __forceinline__ void group_sync() {
+    if (GROUP == 32) __syncwarp(); else __syncthreads();
+}
+template <int GROUP>
 struct coop_smem {
-    static_assert(BLOCK <= 512 && BLOCK % 32 == 0, "a task carries its owner slot in 9 bits");
-    static_assert(RTNW_QL >= 8 * BLOCK && (RTNW_QL & (RTNW_QL - 1)) == 0 && RTNW_QN >= 8 * BLOCK, "queues too small for the block");
-    float4 ray_o[BLOCK];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
-    float4 ray_d[BLOCK];  // d.xyz, w = dot(d,d)
-    float4 ray_i[BLOCK];  // 1/d, w = time
-    uint4 mkey[BLOCK];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
-    hkey_t key[BLOCK];
-    uint32_t q[RTNW_QN];
-    uint32_t ql[RTNW_QL];
+    static_assert(GROUP <= 512 && GROUP % 32 == 0, "a task carries its owner slot in 9 bits");
+    static constexpr int QN = 24 * GROUP;   // node task stack
+    static constexpr int QL = 16 * GROUP;   // gate queue (circular, power of two); node work pauses while < 4*GROUP slots are free
+    static_assert((QL & (QL - 1)) == 0, "the gate ring must be a power of two");
+    float4 ray_o[GROUP];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
+    float4 ray_d[GROUP];  // d.xyz, w = dot(d,d)
+    float4 ray_i[GROUP];  // 1/d, w = time
+    uint4 mkey[GROUP];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
+    hkey_t key[GROUP];
+    uint32_t q[QN];
+    uint32_t ql[QL];
     int n[2];             // node stack height, double-buffered across rounds
-    unsigned lh[2];       // gate queue head (consumed), double-buffered; counts up, index = value % RTNW_QL
+    unsigned lh[2];       // gate queue head (consumed), double-buffered; counts up, index = value % QL
     unsigned lt;          // gate queue tail (produced)
     int overflow;         // a push did not fit (cannot happen for validated scenes); reported to the host
 };
@@ -449,15 +452,16 @@ struct coop_smem {
 // lane from the top of the stack; the remaining warps take one queued gate per lane (leaf->hit for its leaves), so
 // thin node rounds are filled with leaf work instead of idling at the barrier; when the stack is empty all warps
 // drain the gate queue.
-template <int BLOCK, bool COUNT>
-__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLOCK>& sm, int root, int tree_depth, bool active,
+template <int GROUP, bool COUNT>
+__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GROUP>& sm, int root, int tree_depth, bool active,
                                               float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x;
+    constexpr int QN = coop_smem<GROUP>::QN, QL = coop_smem<GROUP>::QL;
+    const int tid = threadIdx.x % GROUP;  // index within the cooperating group
     const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
     if (tid < 2) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
     if (tid == 2) sm.lt = 0u;
-    __syncthreads();
+    group_sync<GROUP>();
     {   // one task per ray: the root of the gate tree
         const unsigned b = __ballot_sync(FULL, active);
         int base = 0;
@@ -465,7 +469,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         base = __shfl_sync(FULL, base, 0);
         if (active) sm.q[base + __popc(b & lt_mask)] = RTNW_TASK(tid, root);
     }
-    __syncthreads();
+    group_sync<GROUP>();
 #pragma unroll 1
     for (int round = 0;; ++round) {
         const int n = sm.n[round & 1];
@@ -473,16 +477,16 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
         const int queued = (int)(ltail - lh);
         if (n == 0 && queued == 0) break;
         // node tasks this round: none while the gate ring is nearly full; otherwise as many as the stack has room for
-        const int room = (RTNW_QN - n - 3 * tree_depth) / 3;
-        const int take = (queued > RTNW_QL - 4 * BLOCK) ? 0 : min(min(n, BLOCK), max(room, 1));
+        const int room = (QN - n - 3 * tree_depth) / 3;
+        const int take = (queued > QL - 4 * GROUP) ? 0 : min(min(n, GROUP), max(room, 1));
         const int base = n - take;
         const int node_threads = (take + 31) & ~31;
-        const int drain = min(queued, BLOCK - node_threads);
+        const int drain = min(queued, GROUP - node_threads);
         uint32_t task = 0;
         if (tid < take) task = sm.q[base + tid];
-        else if (tid >= node_threads && tid - node_threads < drain) task = sm.ql[(lh + (unsigned)(tid - node_threads)) & (RTNW_QL - 1)];
+        else if (tid >= node_threads && tid - node_threads < drain) task = sm.ql[(lh + (unsigned)(tid - node_threads)) & (QL - 1)];
         if (tid == 0) { sm.n[(round + 1) & 1] = base; sm.lh[(round + 1) & 1] = lh + (unsigned)drain; }  // pop both
-        __syncthreads();
+        group_sync<GROUP>();
         const int slot = RTNW_TASK_SLOT(task);
         if (tid < node_threads) {
             // ---- node warps: test the <= 4 child boxes of one wide node per lane, push what passed
@@ -518,15 +522,15 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
             }
             base_n = __shfl_sync(FULL, base_n, 0);
             base_l = __shfl_sync(FULL, base_l, 0);
-            bool ok = (int)(base_l + (unsigned)tl - lh) <= RTNW_QL;  // never laps the unconsumed part of the ring
+            bool ok = (int)(base_l + (unsigned)tl - lh) <= QL;  // never laps the unconsumed part of the ring
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (pass[j]) {
                     if (ref[j] >= 0) {
                         const int at = base_n + __popc(bn[j] & lt_mask);
-                        if (at < RTNW_QN) sm.q[at] = RTNW_TASK(slot, ref[j]); else ok = false;
+                        if (at < QN) sm.q[at] = RTNW_TASK(slot, ref[j]); else ok = false;
                     } else if (ok) {
-                        sm.ql[(base_l + (unsigned)__popc(bl[j] & lt_mask)) & (RTNW_QL - 1)] = RTNW_TASK(slot, ~ref[j]);
+                        sm.ql[(base_l + (unsigned)__popc(bl[j] & lt_mask)) & (QL - 1)] = RTNW_TASK(slot, ~ref[j]);
                     }
                 }
                 base_n += __popc(bn[j]); base_l += (unsigned)__popc(bl[j]);
@@ -549,16 +553,16 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<BLO
             }
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
         }
-        __syncthreads();
+        group_sync<GROUP>();
     }
 }
 
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
 // thread without a ray passes active = false and still works on the other threads' BVH tasks.
-template <int BLOCK, bool COUNT>
-__device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_smem<BLOCK>& sm, const ray_t& wr, bool active,
+template <int GROUP, bool COUNT>
+__device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_smem<GROUP>& sm, const ray_t& wr, bool active,
                                                    float t_min, float t_max, const medium_key& mk, trav_counters& cnt) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x % GROUP;
     sm.key[tid] = RTNW_KEY_NONE;
     sm.mkey[tid] = make_uint4(mk.pixel, mk.sample, mk.depth, 0u);
     int i = 0;
@@ -576,7 +580,7 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
             sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
             sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
             sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-            coop_bvh_item<BLOCK, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt);
+            coop_bvh_item<GROUP, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt);
         } else if (active) {
             float lim = best_t;
 #pragma unroll 1
@@ -591,9 +595,9 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
         }
         i = next;
     }
-    __syncthreads();  // nobody may overwrite sm.key before every owner has read its result
+    group_sync<GROUP>();  // nobody may overwrite sm.key before every owner has read its result
     const hkey_t out = sm.key[tid];
-    __syncthreads();
+    group_sync<GROUP>();
     return out;
 }
 
