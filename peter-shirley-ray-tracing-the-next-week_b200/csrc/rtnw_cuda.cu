@@ -68,6 +68,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     const bool sky = P.p.background == RTNW_BG_SKY;
 
     if (threadIdx.x % RTNW_GROUP == 0) sm.overflow = 0;
+#ifdef RTNW_ROUND_STATS
+    const long long t_start = clock64();
+#endif
     bool alive = true, need = true;
     int pix = -1, k = 0, depth = 0;
     int s_begin = P.p.sample_begin, s_count = P.p.sample_count;  // the samples of the current pixel
@@ -85,7 +88,11 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
         if (alive && need && pix >= 0 && k == s_count) {
             float* dst = P.accum + 3ull * (unsigned long long)pix;
             if (accumulate) { dst[0] += col.x; dst[1] += col.y; dst[2] += col.z; }
+#ifdef RTNW_IMG_CG
+            else { __stcs(dst, col.x); __stcs(dst + 1, col.y); __stcs(dst + 2, col.z); }
+#else
             else { dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; }
+#endif
             pix = -1;
         }
         const bool want = alive && need && pix < 0;
@@ -123,7 +130,14 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
         medium_key mk;
         mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)pix; mk.sample = g.sample; mk.depth = (uint32_t)depth;
         const bool tracing = alive && !need;  // a pixel that owns no sample of this call has no ray (RTNW_F_ROTATE_SAMPLES, ns < G)
+#ifdef RTNW_ROUND_STATS
+        const long long c0 = clock64();
+#endif
         const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt);
+#ifdef RTNW_ROUND_STATS
+        if (threadIdx.x == 0) { RTNW_STAT(10, 1); RTNW_STAT(11, clock64() - c0); }
+        const long long c1 = clock64();
+#endif
         // ---- one level of color(), PSC/main.cpp:25-46, in iterative form
         if (tracing) {
             ++n_rays;
@@ -166,7 +180,13 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                 col = col + L;
             }
         }
+#ifdef RTNW_ROUND_STATS
+        if (threadIdx.x == 0) RTNW_STAT(13, clock64() - c1);
+#endif
     }
+#ifdef RTNW_ROUND_STATS
+    if (threadIdx.x == 0) RTNW_STAT(12, clock64() - t_start);
+#endif
     group_sync<RTNW_GROUP>();
     if (threadIdx.x % RTNW_GROUP == 0 && sm.overflow) atomicAdd(&P.ctr[4], 1ull);
     // work counters: one atomic per warp
@@ -381,6 +401,7 @@ struct stream_builder {
     static float bits(int32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
     static float ubits(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
     static int32_t as_int(float f) { int32_t v; std::memcpy(&v, &f, 4); return v; }
+    static uint32_t as_uint(float f) { uint32_t v; std::memcpy(&v, &f, 4); return v; }
 
     bool bad(const std::string& m) { if (err.empty()) err = m; return false; }
 
@@ -410,7 +431,9 @@ struct stream_builder {
     bool emit_prims(int32_t first, int32_t count, bool first_cont, bool boundary) {
         if (first < 0 || count < 0 || first + count > d.n_prim_slots) return bad("primitive range out of bounds");
         bool cont = first_cont;
+        size_t last_head = (size_t)-1;  // the record a leaf scan tests last (a moving sphere / medium head, not its trailing records)
         for (int32_t s = first; s < first + count; ++s) {
+            last_head = recs.size();
             const rtnw_prim& p = d.prims[s];
             const uint32_t kind = RTNW_KX_KIND(p.kx), flip = RTNW_KX_FLIP(p.kx), chain = RTNW_KX_XFORM(p.kx);
             const int32_t id = (d.prim_ids && !boundary) ? d.prim_ids[s] : -1;
@@ -455,6 +478,7 @@ struct stream_builder {
             }
             cont = true;
         }
+        if (!boundary && last_head != (size_t)-1) recs[last_head].b.z = ubits(as_uint(recs[last_head].b.z) | RTNW_TAG_LAST);
         return true;
     }
 
@@ -722,6 +746,20 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     unsigned long long h[8];
     CUDA_TRY(cudaMemcpyAsync(h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+#ifdef RTNW_ROUND_STATS
+    {
+        unsigned long long rs[32];
+        cudaMemcpyFromSymbol(rs, g_round_stats, sizeof rs);
+        fprintf(stderr, "round_stats rounds %llu take/round %.1f drain/round %.1f n/round %.1f queued/round %.1f pure_gate_rounds %.3f busy<=64 %.3f <=128 %.3f <=192 %.3f >192 %.3f | "
+                        "ray_rounds %llu rounds/ray_round %.1f cycles: hit %.3f (bvh items %.3f) shade %.3f of total; cycles/round by busy<=64 %.0f <=128 %.0f <=192 %.0f >192 %.0f; cycles/ray_round %.0f\n",
+                rs[0], (double)rs[1] / rs[0], (double)rs[2] / rs[0], (double)rs[8] / rs[0], (double)rs[9] / rs[0], (double)rs[3] / rs[0],
+                (double)rs[4] / rs[0], (double)rs[5] / rs[0], (double)rs[6] / rs[0], (double)rs[7] / rs[0], rs[10], (double)rs[0] / rs[10],
+                (double)rs[11] / rs[12], (double)rs[14] / rs[12], (double)rs[13] / rs[12], (double)rs[15] / (rs[4] + 1), (double)rs[16] / (rs[5] + 1),
+                (double)rs[17] / (rs[6] + 1), (double)rs[18] / (rs[7] + 1), (double)rs[12] / rs[10]);
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(g_round_stats, z, sizeof z);
+    }
+#endif
     if (h[4]) return fail(RTNW_ERR_UNSUPPORTED, "BVH task stack overflow: the tree is deeper than RTNW_QN/RTNW_BLOCK - 1 levels");
     if (stats) {
         std::memset(stats, 0, sizeof *stats);

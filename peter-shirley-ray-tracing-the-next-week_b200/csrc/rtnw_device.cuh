@@ -37,6 +37,7 @@ enum rec_kind : uint32_t {
 };
 #define RTNW_TAG_FLIP 16u
 #define RTNW_TAG_CONT 32u  // same narrowing scope as the previous primitive (list semantics, PSC/hitable_list.h:23-29)
+#define RTNW_TAG_LAST 64u  // last primitive of a BVH leaf: the leaf scan ends here without looking at the next record
 #define RTNW_TAG(kind, flip, cont, xf) ((uint32_t)(kind) | ((flip) ? RTNW_TAG_FLIP : 0u) | ((cont) ? RTNW_TAG_CONT : 0u) | ((uint32_t)(xf) << 8))
 
 struct __align__(16) rec {
@@ -202,46 +203,87 @@ __device__ __forceinline__ bool hit_rect(float a0, float a1, float b0, float b1,
     t = tt;
     return true;
 }
-// PSC/box.h:23-38: inner list of six faces, order +z, -z, +y, -y, +x, -x, narrowing from t_hi.
+// PSC/box.h:23-38: inner list of six faces, order +z, -z, +y, -y, +x, -x, narrowing from t_hi.  The six plane distances
+// and extent tests do not depend on the narrowing limit, so they are evaluated first (independent IEEE divisions that
+// interleave); the list's sequential narrowing is then six compare/selects over the same predicates as hit_rect
+// (a NaN t passes every comparison exactly as there).
 __device__ __forceinline__ bool hit_box(f3 p0, f3 p1, const ray_t& r, float t_lo, float t_hi, float& t, int& face) {
+    float tt[6];
+    bool in[6];
+    tt[0] = (p1.z - r.o.z) / r.d.z; tt[1] = (p0.z - r.o.z) / r.d.z;
+    tt[2] = (p1.y - r.o.y) / r.d.y; tt[3] = (p0.y - r.o.y) / r.d.y;
+    tt[4] = (p1.x - r.o.x) / r.d.x; tt[5] = (p0.x - r.o.x) / r.d.x;
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {  // xy faces
+        const float a = r.o.x + tt[f] * r.d.x, b = r.o.y + tt[f] * r.d.y;
+        in[f] = !(a < p0.x || a > p1.x || b < p0.y || b > p1.y);
+    }
+#pragma unroll
+    for (int f = 2; f < 4; ++f) {  // xz faces
+        const float a = r.o.x + tt[f] * r.d.x, b = r.o.z + tt[f] * r.d.z;
+        in[f] = !(a < p0.x || a > p1.x || b < p0.z || b > p1.z);
+    }
+#pragma unroll
+    for (int f = 4; f < 6; ++f) {  // yz faces
+        const float a = r.o.y + tt[f] * r.d.y, b = r.o.z + tt[f] * r.d.z;
+        in[f] = !(a < p0.y || a > p1.y || b < p0.z || b > p1.z);
+    }
     bool any = false;
-    float lim = t_hi, tt;
-    if (hit_rect<2, 0, 1>(p0.x, p1.x, p0.y, p1.y, p1.z, r, t_lo, lim, tt)) { any = true; lim = tt; face = 0; }
-    if (hit_rect<2, 0, 1>(p0.x, p1.x, p0.y, p1.y, p0.z, r, t_lo, lim, tt)) { any = true; lim = tt; face = 1; }
-    if (hit_rect<1, 0, 2>(p0.x, p1.x, p0.z, p1.z, p1.y, r, t_lo, lim, tt)) { any = true; lim = tt; face = 2; }
-    if (hit_rect<1, 0, 2>(p0.x, p1.x, p0.z, p1.z, p0.y, r, t_lo, lim, tt)) { any = true; lim = tt; face = 3; }
-    if (hit_rect<0, 1, 2>(p0.y, p1.y, p0.z, p1.z, p1.x, r, t_lo, lim, tt)) { any = true; lim = tt; face = 4; }
-    if (hit_rect<0, 1, 2>(p0.y, p1.y, p0.z, p1.z, p0.x, r, t_lo, lim, tt)) { any = true; lim = tt; face = 5; }
+    float lim = t_hi;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const bool hit = in[f] & !(tt[f] < t_lo || tt[f] > lim);
+        if (hit) { any = true; lim = tt[f]; face = f; }
+    }
     t = lim;
     return any;
 }
 
 // One surface primitive record (not a medium) against a ray given in the enclosing frame.  `a_frame` is dot(d,d)
 // of that frame; a primitive with its own transform chain recomputes it from the transformed direction.
-__device__ __forceinline__ bool hit_surface(const scene_view& S, int i, float4 A, float4 B, uint32_t tag, const ray_t& r_frame,
-                                            float a_frame, float t_lo, float t_hi, float& t, int& face) {
+// Inlined at its four sites (list scan and gate task, each directly and as a medium boundary).  A single __noinline__
+// copy shrinks k_render from 127 KB to 95 KB of SASS (the L1.5 I-cache holds 32 KB; ncu r9: icc hit rate 91 %) but was
+// measured 4 % slower: the call's register shuffling costs more than the fetches it saves (-DRTNW_SURFACE_INLINE=__noinline__).
+struct surf_hit_t { float t; int face; };  // face < 0: miss
+#ifndef RTNW_SURFACE_INLINE
+#define RTNW_SURFACE_INLINE __forceinline__
+#endif
+__device__ RTNW_SURFACE_INLINE surf_hit_t hit_surface_rec(const rec* __restrict__ recs, const rtnw_xform_op* __restrict__ xforms, int i, float4 A,
+                                                          float4 B, ray_t r, float a, float t_lo, float t_hi) {
+    const uint32_t tag = __float_as_uint(B.z);
     const uint32_t kind = tag & 15u;
     const uint32_t chain = tag >> 8;
-    ray_t r = r_frame;
-    float a = a_frame;
     if (chain) {
-        xform_ray(S.xforms, chain, r);
+        xform_ray(xforms, chain, r);
         a = dot(r.d, r.d);
     }
-    face = 0;
+    surf_hit_t out;
+    out.face = 0;
+    out.t = 0.f;
+    bool hit;
     switch (kind) {
-        case K_SPHERE: return hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_lo, t_hi, t);
+        case K_SPHERE: hit = hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_lo, t_hi, out.t); break;
         case K_MSPHERE: {
-            const float4 A2 = __ldg(&S.recs[i + 1].a);
+            const float4 A2 = __ldg(&recs[i + 1].a);
             const f3 c = moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
-            return hit_sphere(c, A.w, r, a, t_lo, t_hi, t);
+            hit = hit_sphere(c, A.w, r, a, t_lo, t_hi, out.t);
+            break;
         }
-        case K_RECT_XY: return hit_rect<2, 0, 1>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, t);
-        case K_RECT_XZ: return hit_rect<1, 0, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, t);
-        case K_RECT_YZ: return hit_rect<0, 1, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, t);
-        case K_BOX: return hit_box(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, t_lo, t_hi, t, face);
-        default: return false;
+        case K_RECT_XY: hit = hit_rect<2, 0, 1>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
+        case K_RECT_XZ: hit = hit_rect<1, 0, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
+        case K_RECT_YZ: hit = hit_rect<0, 1, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
+        case K_BOX: hit = hit_box(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, t_lo, t_hi, out.t, out.face); break;
+        default: hit = false; break;
     }
+    if (!hit) out.face = -1;
+    return out;
+}
+__device__ __forceinline__ bool hit_surface(const scene_view& S, int i, float4 A, float4 B, uint32_t tag, const ray_t& r_frame,
+                                            float a_frame, float t_lo, float t_hi, float& t, int& face) {
+    const surf_hit_t h = hit_surface_rec(S.recs, S.xforms, i, A, B, r_frame, a_frame, t_lo, t_hi);
+    t = h.t;
+    face = h.face < 0 ? 0 : h.face;
+    return h.face >= 0;
 }
 
 // boundary->hit(r, t_lo, t_hi, rec) of a constant_medium: list semantics over the nb boundary records that follow it
@@ -373,22 +415,28 @@ __device__ __forceinline__ int test_record(const scene_view& S, int i, float4 A,
 // A leaf of a bvh_node (one hitable, possibly a list of several primitives): tested with the UN-narrowed range the
 // node received, narrowing only inside the leaf (PSC/bvh.h:34-35, PSC/hitable_list.h:23-29).  Returns its candidate key.
 template <bool COUNT>
-__device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, const ray_t& r, float a, float t_min, float tmax0,
-                                            const medium_key& mk, trav_counters& cnt) {
+__device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, float4 A, float4 B, const ray_t& r, float a, float t_min,
+                                            float tmax0, const medium_key& mk, trav_counters& cnt) {
     hkey_t best = RTNW_KEY_NONE;
     float lim = tmax0;
-    int i = first;
+    int i = first;  // A, B: record `first`, loaded by the caller (both leaves of a gate are fetched before either is tested)
     for (;;) {
-        const float4 A = __ldg(&S.recs[i].a), B = __ldg(&S.recs[i].b);
         bool hit; float t; int face;
         const int step = test_record<COUNT>(S, i, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
         if (hit) { lim = t; best = make_key(t, i, face); }  // inside a list the later accepted hit always replaces
+        if (__float_as_uint(B.z) & RTNW_TAG_LAST) break;
         i += step;
-        const uint32_t tag = __float_as_uint(__ldg(&S.recs[i].b).z);
-        if (!(tag & RTNW_TAG_CONT) || (tag & 15u) >= K_NODE) break;
+        A = __ldg(&S.recs[i].a); B = __ldg(&S.recs[i].b);
     }
     return best;
 }
+
+#ifdef RTNW_ROUND_STATS  // tuning aid (never defined in the product build): shape of the cooperative rounds
+__device__ unsigned long long g_round_stats[32];
+#define RTNW_STAT(i, v) atomicAdd(&g_round_stats[i], (unsigned long long)(v))
+#else
+#define RTNW_STAT(i, v) ((void)0)
+#endif
 
 // ---- block-cooperative closest hit --------------------------------------------------------------------------
 // Every thread of the block owns one ray (or none).  All rays walk the same record stream, item by item:
@@ -421,19 +469,24 @@ template <int GROUP>
 __device__ __forceinline__ void group_sync() {
     if (GROUP == 32) __syncwarp(); else __syncthreads();
 }
+#ifndef RTNW_QN_MULT
+#define RTNW_QN_MULT 24
+#endif
+#ifndef RTNW_QL_MULT
+#define RTNW_QL_MULT 16
+#endif
 template <int GROUP>
 struct coop_smem {
     static_assert(GROUP <= 512 && GROUP % 32 == 0, "a task carries its owner slot in 9 bits");
-    static constexpr int QN = 24 * GROUP;   // node task stack
-    static constexpr int QL = 16 * GROUP;   // gate queue (circular, power of two); node work pauses while < 4*GROUP slots are free
+    static constexpr int QN = RTNW_QN_MULT * GROUP;   // node task stack
+    static constexpr int QL = RTNW_QL_MULT * GROUP;   // gate queue (circular, power of two); node work pauses while < 4*GROUP slots are free
     static_assert((QL & (QL - 1)) == 0, "the gate ring must be a power of two");
     float4 ray_o[GROUP];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
     float4 ray_d[GROUP];  // d.xyz, w = dot(d,d)
     float4 ray_i[GROUP];  // 1/d, w = time
     uint4 mkey[GROUP];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
     hkey_t key[GROUP];
-    uint32_t q[QN];
-    uint32_t ql[QL];
+    uint32_t q[QN + QL];  // [0, QN): node task stack; [QN, QN + QL): gate ring (one array: a push is a single predicated store)
     int n[2];             // node stack height, double-buffered across rounds
     unsigned lh[2];       // gate queue head (consumed), double-buffered; counts up, index = value % QL
     unsigned lt;          // gate queue tail (produced)
@@ -459,6 +512,9 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
     constexpr int QN = coop_smem<GROUP>::QN, QL = coop_smem<GROUP>::QL;
     const int tid = threadIdx.x % GROUP;  // index within the cooperating group
     const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+#ifdef RTNW_ROUND_STATS
+    int stat_busy = 0; long long stat_c = 0; const long long stat_c0 = clock64();
+#endif
     if (tid < 2) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
     if (tid == 2) sm.lt = 0u;
     group_sync<GROUP>();
@@ -484,34 +540,43 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
         const int drain = min(queued, GROUP - node_threads);
         uint32_t task = 0;
         if (tid < take) task = sm.q[base + tid];
-        else if (tid >= node_threads && tid - node_threads < drain) task = sm.ql[(lh + (unsigned)(tid - node_threads)) & (QL - 1)];
+        else if (tid >= node_threads && tid - node_threads < drain) task = sm.q[QN + ((lh + (unsigned)(tid - node_threads)) & (QL - 1))];
         if (tid == 0) { sm.n[(round + 1) & 1] = base; sm.lh[(round + 1) & 1] = lh + (unsigned)drain; }  // pop both
+#ifdef RTNW_ROUND_STATS
+        if (tid == 0) {
+            RTNW_STAT(0, 1); RTNW_STAT(1, take); RTNW_STAT(2, drain); RTNW_STAT(8, n); RTNW_STAT(9, queued);
+            if (take == 0) RTNW_STAT(3, 1);
+            const int busy = node_threads + drain;
+            RTNW_STAT(busy <= 64 ? 4 : busy <= 128 ? 5 : busy <= 192 ? 6 : 7, 1);
+            stat_busy = busy; stat_c = clock64();
+        }
+#endif
         group_sync<GROUP>();
         const int slot = RTNW_TASK_SLOT(task);
         if (tid < node_threads) {
-            // ---- node warps: test the <= 4 child boxes of one wide node per lane, push what passed
-            int ref[4] = {RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE, RTNW_REF_NONE};
-            bool pass[4] = {false, false, false, false};
-            if (tid < take) {
-                const float4* N = S.wnodes + 8 * (size_t)RTNW_TASK_IDX(task);
-                const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
-                const float4 rf = __ldg(N + 6);
-                const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
-                const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
-                ref[0] = __float_as_int(rf.x); ref[1] = __float_as_int(rf.y); ref[2] = __float_as_int(rf.z); ref[3] = __float_as_int(rf.w);
-                pass[0] = ref[0] != RTNW_REF_NONE && hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, ro.w);
-                pass[1] = ref[1] != RTNW_REF_NONE && hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, ro.w);
-                pass[2] = ref[2] != RTNW_REF_NONE && hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, ro.w);
-                pass[3] = ref[3] != RTNW_REF_NONE && hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, ro.w);
-                if (COUNT) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
-            }
-            // warp-aggregated appends: wide nodes back onto the stack, gates to the gate queue
+            // ---- node warps: test the <= 4 child boxes of one wide node per lane, push what passed.  Straight-line code
+            // (no short-circuit): the four slab tests are independent and interleave; a lane of the last node warp
+            // without a task reads node 0 / slot 0 and masks its results.
+            const bool live = tid < take;
+            const float4* N = S.wnodes + 8 * (size_t)(live ? RTNW_TASK_IDX(task) : 0u);
+            const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
+            const float4 rf = __ldg(N + 6);
+            const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
+            const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
+            const int ref[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
+            bool pass[4];
+            pass[0] = live & (ref[0] != RTNW_REF_NONE) & hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, ro.w);
+            pass[1] = live & (ref[1] != RTNW_REF_NONE) & hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, ro.w);
+            pass[2] = live & (ref[2] != RTNW_REF_NONE) & hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, ro.w);
+            pass[3] = live & (ref[3] != RTNW_REF_NONE) & hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, ro.w);
+            if (COUNT && live) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
+            // warp-aggregated appends: wide nodes back onto the stack, gates to the gate ring
             unsigned bn[4], bl[4];
             int tn = 0, tl = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                bn[j] = __ballot_sync(FULL, pass[j] && ref[j] >= 0);
-                bl[j] = __ballot_sync(FULL, pass[j] && ref[j] < 0);
+                bn[j] = __ballot_sync(FULL, pass[j] & (ref[j] >= 0));
+                bl[j] = __ballot_sync(FULL, pass[j] & (ref[j] < 0));
                 tn += __popc(bn[j]); tl += __popc(bl[j]);
             }
             int base_n = 0;
@@ -522,23 +587,24 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             }
             base_n = __shfl_sync(FULL, base_n, 0);
             base_l = __shfl_sync(FULL, base_l, 0);
-            bool ok = (int)(base_l + (unsigned)tl - lh) <= QL;  // never laps the unconsumed part of the ring
+            const bool ring_ok = (int)(base_l + (unsigned)tl - lh) <= QL;  // never laps the unconsumed part of the ring
+            bool ok = true;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (pass[j]) {
-                    if (ref[j] >= 0) {
-                        const int at = base_n + __popc(bn[j] & lt_mask);
-                        if (at < QN) sm.q[at] = RTNW_TASK(slot, ref[j]); else ok = false;
-                    } else if (ok) {
-                        sm.ql[(base_l + (unsigned)__popc(bl[j] & lt_mask)) & (QL - 1)] = RTNW_TASK(slot, ~ref[j]);
-                    }
-                }
+                const bool isn = ref[j] >= 0;
+                const int at_n = base_n + __popc(bn[j] & lt_mask);
+                const int at_l = QN + (int)((base_l + (unsigned)__popc(bl[j] & lt_mask)) & (unsigned)(QL - 1));
+                const bool fits = isn ? at_n < QN : ring_ok;
+                if (pass[j] & fits) sm.q[isn ? at_n : at_l] = RTNW_TASK(slot, isn ? ref[j] : ~ref[j]);
+                ok &= !pass[j] | fits;
                 base_n += __popc(bn[j]); base_l += (unsigned)__popc(bl[j]);
             }
             if (!ok) sm.overflow = 1;
         } else if (tid - node_threads < drain) {
             // ---- gate lanes: leaf->hit(r, tmin, tmax0) for the one or two leaves the gate guards
             const int2 g = __ldg(&S.gates[RTNW_TASK_IDX(task)]);
+            const int g1 = g.y >= 0 ? g.y : g.x;
+            const float4 A0 = __ldg(&S.recs[g.x].a), B0 = __ldg(&S.recs[g.x].b), A1 = __ldg(&S.recs[g1].a), B1 = __ldg(&S.recs[g1].b);
             const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
             const uint4 mq = sm.mkey[slot];
             ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
@@ -548,13 +614,19 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             for (int w = 0; w < 2; ++w) {  // one copy of the leaf code
                 const int leaf = w ? g.y : g.x;
                 if (leaf < 0) break;
-                const hkey_t k2 = test_leaf<COUNT>(S, leaf, r, rd.w, t_min, ro.w, mk, cnt);
+                const hkey_t k2 = test_leaf<COUNT>(S, leaf, w ? A1 : A0, w ? B1 : B0, r, rd.w, t_min, ro.w, mk, cnt);
                 if (k2 < k) k = k2;
             }
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
         }
         group_sync<GROUP>();
+#ifdef RTNW_ROUND_STATS
+        if (tid == 0) { const long long d = clock64() - stat_c; RTNW_STAT(stat_busy <= 64 ? 15 : stat_busy <= 128 ? 16 : stat_busy <= 192 ? 17 : 18, d); }
+#endif
     }
+#ifdef RTNW_ROUND_STATS
+    if (tid == 0) RTNW_STAT(14, clock64() - stat_c0);
+#endif
 }
 
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
@@ -740,7 +812,11 @@ __device__ __forceinline__ f3 texture_value(const scene_view& S, int tex, float 
         if (i > nx - 1) i = nx - 1;
         if (j > ny - 1) j = ny - 1;
         const uint8_t* px = S.images + off + 3 * i + 3 * nx * j;
+#ifdef RTNW_IMG_CG  // texels bypass L1: the image (MBs, random access) would evict the node / record working set
+        return mk3((float)__ldcg(px) / 255.0f, (float)__ldcg(px + 1) / 255.0f, (float)__ldcg(px + 2) / 255.0f);
+#else
         return mk3((float)__ldg(px) / 255.0f, (float)__ldg(px + 1) / 255.0f, (float)__ldg(px + 2) / 255.0f);
+#endif
     }
 }
 
