@@ -537,16 +537,16 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
         const int take = (queued > QL - 4 * GROUP) ? 0 : min(min(n, GROUP), max(room, 1));
         const int base = n - take;
         const int node_threads = (take + 31) & ~31;
-        const int drain = min(queued, GROUP - node_threads);
+        const int drain = min(queued, (GROUP - node_threads) >> 1);  // gates taken this round: TWO lanes each, one per leaf
         uint32_t task = 0;
         if (tid < take) task = sm.q[base + tid];
-        else if (tid >= node_threads && tid - node_threads < drain) task = sm.q[QN + ((lh + (unsigned)(tid - node_threads)) & (QL - 1))];
+        else if (tid >= node_threads && tid - node_threads < 2 * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> 1)) & (QL - 1))];
         if (tid == 0) { sm.n[(round + 1) & 1] = base; sm.lh[(round + 1) & 1] = lh + (unsigned)drain; }  // pop both
 #ifdef RTNW_ROUND_STATS
         if (tid == 0) {
             RTNW_STAT(0, 1); RTNW_STAT(1, take); RTNW_STAT(2, drain); RTNW_STAT(8, n); RTNW_STAT(9, queued);
             if (take == 0) RTNW_STAT(3, 1);
-            const int busy = node_threads + drain;
+            const int busy = node_threads + 2 * drain;
             RTNW_STAT(busy <= 64 ? 4 : busy <= 128 ? 5 : busy <= 192 ? 6 : 7, 1);
             stat_busy = busy; stat_c = clock64();
         }
@@ -600,22 +600,19 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
                 base_n += __popc(bn[j]); base_l += (unsigned)__popc(bl[j]);
             }
             if (!ok) sm.overflow = 1;
-        } else if (tid - node_threads < drain) {
-            // ---- gate lanes: leaf->hit(r, tmin, tmax0) for the one or two leaves the gate guards
+        } else if (tid - node_threads < 2 * drain) {
+            // ---- gate lanes: leaf->hit(r, tmin, tmax0) for the one or two leaves the gate guards, one lane per leaf (a leaf
+            // test is about as long as a node task; a round lasts as long as its slowest lane)
             const int2 g = __ldg(&S.gates[RTNW_TASK_IDX(task)]);
-            const int g1 = g.y >= 0 ? g.y : g.x;
-            const float4 A0 = __ldg(&S.recs[g.x].a), B0 = __ldg(&S.recs[g.x].b), A1 = __ldg(&S.recs[g1].a), B1 = __ldg(&S.recs[g1].b);
-            const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
-            const uint4 mq = sm.mkey[slot];
-            ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
-            medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
+            const int leaf = (tid & 1) ? g.y : g.x;  // node_threads is even: lane parity = leaf of the gate
             hkey_t k = RTNW_KEY_NONE;
-#pragma unroll 1
-            for (int w = 0; w < 2; ++w) {  // one copy of the leaf code
-                const int leaf = w ? g.y : g.x;
-                if (leaf < 0) break;
-                const hkey_t k2 = test_leaf<COUNT>(S, leaf, w ? A1 : A0, w ? B1 : B0, r, rd.w, t_min, ro.w, mk, cnt);
-                if (k2 < k) k = k2;
+            if (leaf >= 0) {
+                const float4 A0 = __ldg(&S.recs[leaf].a), B0 = __ldg(&S.recs[leaf].b);
+                const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
+                const uint4 mq = sm.mkey[slot];
+                ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+                medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
+                k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, ro.w, mk, cnt);
             }
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
         }
