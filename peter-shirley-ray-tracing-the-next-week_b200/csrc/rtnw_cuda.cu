@@ -35,6 +35,8 @@ struct render_args {
     rtnw_camera cam;
     rtnw_render_params p;
     float* accum;                 // nx*ny*3 sums, index (j*nx+i)*3+c
+    float* chunk_sums;            // chunks > 1: chunks * nx*ny*3 partial sums, summed in chunk order by k_sum_chunks
+    int chunks;                   // each pixel's samples are cut into this many contiguous ranges, one work item each
     unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests, [4] task stack overflows
 };
 
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     const long long t_start = clock64();
 #endif
     bool alive = true, need = true;
-    int pix = -1, k = 0, depth = 0;
+    int pix = -1, k = 0, depth = 0, chunk = 0;
     int s_begin = P.p.sample_begin, s_count = P.p.sample_count;  // the samples of the current pixel
     f3 col = mk3(0.f, 0.f, 0.f), L = col, T = col;
     ray_t wr;
@@ -86,13 +88,14 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     for (;;) {
         // ---- next sample of the pixel, or next pixel, PSC/main.cpp:299-308
         if (alive && need && pix >= 0 && k == s_count) {
-            float* dst = P.accum + 3ull * (unsigned long long)pix;
-            if (accumulate) { dst[0] += col.x; dst[1] += col.y; dst[2] += col.z; }
-#ifdef RTNW_IMG_CG
-            else { __stcs(dst, col.x); __stcs(dst + 1, col.y); __stcs(dst + 2, col.z); }
-#else
-            else { dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; }
-#endif
+            if (P.chunks > 1) {  // partial sum of one sample range; k_sum_chunks adds the ranges up in order
+                float* dst = P.chunk_sums + 3ull * ((unsigned long long)chunk * (unsigned long long)(nx * ny) + (unsigned long long)pix);
+                dst[0] = col.x; dst[1] = col.y; dst[2] = col.z;
+            } else {
+                float* dst = P.accum + 3ull * (unsigned long long)pix;
+                if (accumulate) { dst[0] += col.x; dst[1] += col.y; dst[2] += col.z; }
+                else { dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; }
+            }
             pix = -1;
         }
         const bool want = alive && need && pix < 0;
@@ -104,13 +107,19 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             base = __shfl_sync(FULL, base, leader);
             if (want) {
                 const unsigned long long mine = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-                if (mine >= npix) alive = false;
+                if (mine >= npix * (unsigned long long)P.chunks) alive = false;
                 else {
-                    pix = P.p.pixel_begin + (int)mine * P.p.pixel_stride; k = 0; col = mk3(0.f, 0.f, 0.f);
+                    chunk = (int)(mine / npix);  // work item = (sample range, pixel), range-major
+                    pix = P.p.pixel_begin + (int)(mine % npix) * P.p.pixel_stride; k = 0; col = mk3(0.f, 0.f, 0.f);
+                    s_count = P.p.sample_count;
                     if (rotate) {  // RTNW_F_ROTATE_SAMPLES: ownership of the samples rotates with the pixel index
                         const int g = P.p.sample_stride;
                         s_begin = ((P.p.sample_begin - pix) % g + g) % g;
                         s_count = s_begin < P.p.sample_count ? (P.p.sample_count - s_begin + g - 1) / g : 0;
+                    }
+                    if (P.chunks > 1) {  // this item's range of the pixel's samples: k in [chunk*n/C, (chunk+1)*n/C)
+                        k = (int)((long long)chunk * s_count / P.chunks);
+                        s_count = (int)((long long)(chunk + 1) * s_count / P.chunks);
                     }
                 }
             }
@@ -259,6 +268,21 @@ __global__ void k_quantize(const float* __restrict__ sums, int nx, int ny, float
     }
 }
 
+// chunks > 1: a pixel's sum = its sample ranges' partial sums added in range order (deterministic; differs from the
+// single-range sum only by float reassociation, like the multi-GPU split)
+__global__ void k_sum_chunks(const float* __restrict__ parts, int chunks, unsigned long long plane, int pixel_begin, int pixel_stride,
+                             int pixel_count, int accumulate, float* __restrict__ accum) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= pixel_count) return;
+    const unsigned long long at = 3ull * (unsigned long long)(pixel_begin + q * pixel_stride);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = parts[at + c];
+        for (int r = 1; r < chunks; ++r) v += parts[(unsigned long long)r * plane + at + c];
+        if (accumulate) accum[at + c] += v; else accum[at + c] = v;
+    }
+}
+
 // FP32 issue peak of the device, measured: 8 independent FFMA chains per thread (the roofline denominator of bench.py)
 __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -371,6 +395,8 @@ struct rtnw_ctx {
     int sm_count = 0, clock_khz = 0, smem_optin = 0, l2_bytes = 0;
     float* accum = nullptr;          // device accumulation buffer of rtnw_render
     size_t accum_floats = 0;
+    float* chunk_sums = nullptr;     // partial sums of the sample-range split (small images)
+    size_t chunk_floats = 0;
     unsigned long long* ctr = nullptr;  // 4 device counters
     int blocks_per_sm[2] = {0, 0};
     // freed scene slabs are kept for the next upload (cudaMalloc/cudaFree synchronise the device and can take
@@ -698,22 +724,45 @@ int check_ctx(rtnw_ctx* ctx) {
     return RTNW_OK;
 }
 
+// resident blocks per SM of k_render<COUNT> (cached per context)
 template <bool COUNT>
-int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
+int render_occupancy(rtnw_ctx* ctx, int* out) {
     int& bps = ctx->blocks_per_sm[COUNT ? 1 : 0];
     if (bps == 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_render<COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT>, RTNW_BLOCK, sizeof(block_smem)));
         if (bps < 1) bps = 1;
     }
+    *out = bps;
+    return RTNW_OK;
+}
+
+template <bool COUNT>
+int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
+    int bps = 0;
+    const int rc = render_occupancy<COUNT>(ctx, &bps);
+    if (rc != RTNW_OK) return rc;
     int blocks = ctx->sm_count * bps;
-    const long long warps_needed = ((long long)a.p.pixel_count + 31) / 32;
+    const long long warps_needed = ((long long)a.p.pixel_count * a.chunks + 31) / 32;
     const long long blocks_needed = (warps_needed * 32 + RTNW_BLOCK - 1) / RTNW_BLOCK;
     if (blocks_needed < blocks) blocks = (int)blocks_needed;
     if (const char* e = getenv("RTNW_GRID_BLOCKS")) { const int v = atoi(e); if (v > 0) blocks = v; }
     k_render<COUNT><<<blocks, RTNW_BLOCK, sizeof(block_smem), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RTNW_OK;
+}
+
+// One thread owns one pixel, so an image with fewer pixels than the device has resident threads (the reference's own
+// 200x100 default is 20 000) would leave most of it idle.  Such a call cuts every pixel's samples into `chunks`
+// contiguous ranges, one work item each; their partial sums are added up in range order by k_sum_chunks.
+int pick_chunks(rtnw_ctx* ctx, const rtnw_render_params& p, int bps) {
+    if (const char* e = getenv("RTNW_SAMPLE_CHUNKS")) { const int v = atoi(e); if (v > 0) return std::min(v, 256); }
+    const long long threads = (long long)ctx->sm_count * bps * RTNW_BLOCK;
+    if ((long long)p.pixel_count >= threads) return 1;
+    int per_pixel = p.sample_count;  // samples of a pixel in this call (ROTATE: sample_count is the frame's total over sample_stride ranks)
+    if (p.flags & RTNW_F_ROTATE_SAMPLES) per_pixel = p.sample_count / p.sample_stride;
+    const long long want = (2 * threads + p.pixel_count - 1) / p.pixel_count;  // about two work items per resident thread
+    return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(want, per_pixel / 4), 64));  // >= 4 samples per item
 }
 
 int validate_params(const rtnw_render_params* p) {
@@ -738,10 +787,35 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     if (a.p.pixel_count == 0) { a.p.pixel_begin = 0; a.p.pixel_stride = 1; a.p.pixel_count = p->nx * p->ny; }
     a.accum = accum_dev;
     a.ctr = ctx->ctr;
+    int bps = 0;
+    int rc = (p->flags & RTNW_F_COUNTERS) ? render_occupancy<true>(ctx, &bps) : render_occupancy<false>(ctx, &bps);
+    if (rc != RTNW_OK) return rc;
+    a.chunks = pick_chunks(ctx, a.p, bps);
+    a.chunk_sums = nullptr;
+    const size_t plane = (size_t)p->nx * p->ny * 3;
+    if (a.chunks > 1) {
+        if (ctx->chunk_floats < plane * a.chunks) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (ctx->chunk_sums) cudaFree(ctx->chunk_sums);
+            ctx->chunk_sums = nullptr;
+            ctx->chunk_floats = 0;
+            if (cudaMalloc(&ctx->chunk_sums, plane * a.chunks * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(RTNW_ERR_NOMEM, "cudaMalloc of the sample-range partial sums failed");
+            }
+            ctx->chunk_floats = plane * a.chunks;
+        }
+        a.chunk_sums = ctx->chunk_sums;
+    }
     CUDA_TRY(cudaMemsetAsync(ctx->ctr, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-    const int rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true>(ctx, a, st) : launch_render<false>(ctx, a, st);
+    rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true>(ctx, a, st) : launch_render<false>(ctx, a, st);
     if (rc != RTNW_OK) return rc;
+    if (a.chunks > 1) {
+        k_sum_chunks<<<(a.p.pixel_count + 255) / 256, 256, 0, st>>>(a.chunk_sums, a.chunks, (unsigned long long)plane, a.p.pixel_begin,
+                                                                   a.p.pixel_stride, a.p.pixel_count, (p->flags & RTNW_F_ACCUMULATE) ? 1 : 0, accum_dev);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaEventRecord(ctx->ev1, st));
     unsigned long long h[8];
     CUDA_TRY(cudaMemcpyAsync(h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -787,7 +861,7 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
         stats->box_tests = h[2];
         stats->prim_tests = h[3];
         CUDA_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev0, ctx->ev1));
-        stats->kernel_launches = 1;
+        stats->kernel_launches = a.chunks > 1 ? 2 : 1;
     }
     return RTNW_OK;
 }
@@ -845,6 +919,7 @@ int rtnw_ctx_destroy(rtnw_ctx* c) {
     if (!c) return RTNW_OK;
     cudaSetDevice(c->device);
     if (c->accum) cudaFree(c->accum);
+    if (c->chunk_sums) cudaFree(c->chunk_sums);
     for (int q = 0; q < 2; ++q) if (c->spare_slab[q]) cudaFree(c->spare_slab[q]);
     if (c->ctr) cudaFree(c->ctr);
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -809,11 +809,7 @@ __device__ __forceinline__ f3 texture_value(const scene_view& S, int tex, float 
         if (i > nx - 1) i = nx - 1;
         if (j > ny - 1) j = ny - 1;
         const uint8_t* px = S.images + off + 3 * i + 3 * nx * j;
-#ifdef RTNW_IMG_CG  // texels bypass L1: the image (MBs, random access) would evict the node / record working set
-        return mk3((float)__ldcg(px) / 255.0f, (float)__ldcg(px + 1) / 255.0f, (float)__ldcg(px + 2) / 255.0f);
-#else
         return mk3((float)__ldg(px) / 255.0f, (float)__ldg(px + 1) / 255.0f, (float)__ldg(px + 2) / 255.0f);
-#endif
     }
 }
 

@@ -357,6 +357,38 @@ def test_rotated_sample_split_is_an_even_partition(rtnw, ctx, ns, world):
     ds.close()
 
 
+def test_small_image_sample_ranges(rtnw, ctx, monkeypatch):
+    """An image with fewer pixels than the device has resident threads is rendered as (sample range, pixel) work items
+    whose partial sums are added in range order: same paths, same rays, the sums equal up to float reassociation, and
+    still bitwise reproducible.  RTNW_SAMPLE_CHUNKS forces the number of ranges (1 = one thread per pixel)."""
+    import torch
+    hs = rtnw.HostScene("cornell_smoke")
+    ds = ctx.upload(hs.desc_ptr)
+    nx, ny, ns = 64, 48, 37
+    cam = hs.camera(nx, ny)
+    monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", "1")
+    one, s1 = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4))
+    assert s1.kernel_launches == 1
+    for forced in (None, "5", "64"):
+        if forced is None:
+            monkeypatch.delenv("RTNW_SAMPLE_CHUNKS")
+        else:
+            monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", forced)
+        a, sa = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4))
+        b, sb = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4))
+        assert sa.kernel_launches == 2 and sa.paths == s1.paths and sa.rays == s1.rays == sb.rays
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.allclose(a, one, rtol=1e-5, atol=1e-6)
+    # with the multi-GPU split and accumulation on top
+    monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", "3")
+    acc = torch.zeros((ny, nx, 3), dtype=torch.float32, device="cuda")
+    for g in range(2):
+        ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4, sample_begin=g, sample_stride=2,
+                                        flags_extra=rtnw.F_ROTATE_SAMPLES | rtnw.F_ACCUMULATE), acc.data_ptr())
+    assert np.allclose(acc.cpu().numpy(), one, rtol=1e-5, atol=1e-6)
+    ds.close()
+
+
 def test_device_epilogue_equals_host_epilogue(rtnw, ctx):
     """rtnw_quantize_device (gamma + quantise + clamp on the GPU, after the reduce) is bit-identical to the host epilogue
     rtnw_host_quantize, which restates PSC/main.cpp:315-325; includes values > 1 (light), 0 and NaN-free negatives."""
