@@ -332,10 +332,11 @@ def main():
             "per_rank_ms": {"kernel": [r[0] for r in per_rank], "step": [r[1] for r in per_rank]},
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch, ncu --set full capture
-                         # profiles/round1_r8_northstar_ncu_summary.txt: the scene tables are read once; the 12 MB image is
-                         # still dirty in the 126 MB L2 when the kernel ends, so it does not show as DRAM writes
-                         "traffic": 1640192, "kernel": "k_render", "kernel_ms": 1e3 * kernel_s, "flop_per_ray": f_ray,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch of THIS workload (ncu capture of
+                         # `bench.py --steps 1 --warmup 1`, profiles/round1_r12_bench_dram_traffic.csv): the scene tables and the
+                         # image texture are read once; the 12 MB image is still dirty in the 126 MB L2 when the kernel ends,
+                         # so it does not show as DRAM writes
+                         "traffic": 2415360, "kernel": "k_render", "kernel_ms": 1e3 * kernel_s, "flop_per_ray": f_ray,
                          "peak_source": f"measured FFMA microbenchmark on this GPU (nominal {fp32_nominal:.1f} = {info['sm_count']} SM x "
                                         f"128 lanes x 2 x {sm_mhz:.0f} MHz)",
                          "note": "FP32-issue bound, not HBM/tensor: the scene (<2 MB) lives in L1/L2; see the hbm sub-object",
