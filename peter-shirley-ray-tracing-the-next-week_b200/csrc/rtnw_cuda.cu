@@ -752,17 +752,20 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
     return RTNW_OK;
 }
 
-// One thread owns one pixel, so an image with fewer pixels than the device has resident threads (the reference's own
-// 200x100 default is 20 000) would leave most of it idle.  Such a call cuts every pixel's samples into `chunks`
-// contiguous ranges, one work item each; their partial sums are added up in range order by k_sum_chunks.
-int pick_chunks(rtnw_ctx* ctx, const rtnw_render_params& p, int bps) {
+// One thread owns one (pixel, sample range) work item at a time.  With whole pixels as items (one range) the kernel ends
+// in a tail as long as the most expensive pixel — at 100 spp about 14 ms of 220, during which most of the device idles —
+// and an image with fewer pixels than the device has resident threads (the reference's own 200x100 default is 20 000)
+// never fills it.  So every pixel's samples are cut into `chunks` contiguous ranges of at least four samples; a
+// range's partial sum goes to its own plane and k_sum_chunks adds the planes up in range order (reproducible bit for
+// bit; differs from the one-range sum only by float reassociation, like the multi-GPU split).  Measured on the bench
+// workload: 453 (1 range) / 477 (2) / 490 (4) / 498 (16) Mpaths/s.
+int pick_chunks(const rtnw_render_params& p) {
     if (const char* e = getenv("RTNW_SAMPLE_CHUNKS")) { const int v = atoi(e); if (v > 0) return std::min(v, 256); }
-    const long long threads = (long long)ctx->sm_count * bps * RTNW_BLOCK;
-    if ((long long)p.pixel_count >= threads) return 1;
     int per_pixel = p.sample_count;  // samples of a pixel in this call (ROTATE: sample_count is the frame's total over sample_stride ranks)
     if (p.flags & RTNW_F_ROTATE_SAMPLES) per_pixel = p.sample_count / p.sample_stride;
-    const long long want = (2 * threads + p.pixel_count - 1) / p.pixel_count;  // about two work items per resident thread
-    return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(want, per_pixel / 4), 64));  // >= 4 samples per item
+    const long long plane_bytes = (long long)p.nx * p.ny * 3 * (long long)sizeof(float);
+    const long long by_memory = std::max<long long>(1, (1ll << 30) / plane_bytes);  // at most 1 GiB of partial sums
+    return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(per_pixel / 4, 32), by_memory));
 }
 
 int validate_params(const rtnw_render_params* p) {
@@ -787,10 +790,8 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     if (a.p.pixel_count == 0) { a.p.pixel_begin = 0; a.p.pixel_stride = 1; a.p.pixel_count = p->nx * p->ny; }
     a.accum = accum_dev;
     a.ctr = ctx->ctr;
-    int bps = 0;
-    int rc = (p->flags & RTNW_F_COUNTERS) ? render_occupancy<true>(ctx, &bps) : render_occupancy<false>(ctx, &bps);
-    if (rc != RTNW_OK) return rc;
-    a.chunks = pick_chunks(ctx, a.p, bps);
+    int rc = RTNW_OK;
+    a.chunks = pick_chunks(a.p);
     a.chunk_sums = nullptr;
     const size_t plane = (size_t)p->nx * p->ny * 3;
     if (a.chunks > 1) {

@@ -358,7 +358,7 @@ def test_rotated_sample_split_is_an_even_partition(rtnw, ctx, ns, world):
 
 
 def test_small_image_sample_ranges(rtnw, ctx, monkeypatch):
-    """An image with fewer pixels than the device has resident threads is rendered as (sample range, pixel) work items
+    """A pixel with enough samples is rendered as several (sample range, pixel) work items
     whose partial sums are added in range order: same paths, same rays, the sums equal up to float reassociation, and
     still bitwise reproducible.  RTNW_SAMPLE_CHUNKS forces the number of ranges (1 = one thread per pixel)."""
     import torch
