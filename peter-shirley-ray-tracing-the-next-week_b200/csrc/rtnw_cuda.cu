@@ -29,6 +29,8 @@ using namespace rtnw_dev;
 static_assert(RTNW_GROUP == RTNW_BLOCK || RTNW_GROUP == 32,
               "cooperating group = the whole block (__syncthreads) or one warp (__syncwarp); other sizes would need named barriers");
 
+#define RTNW_MAX_CHUNKS 64
+
 // ================================================================================================ kernels
 struct render_args {
     scene_view S;
@@ -37,6 +39,8 @@ struct render_args {
     float* accum;                 // nx*ny*3 sums, index (j*nx+i)*3+c
     float* chunk_sums;            // chunks > 1: chunks * nx*ny*3 partial sums, summed in chunk order by k_sum_chunks
     int chunks;                   // each pixel's samples are cut into this many contiguous ranges, one work item each
+    int chunk_total;              // range c of a pixel with n samples: k in [cum[c]*n/total, cum[c+1]*n/total)
+    int chunk_cum[RTNW_MAX_CHUNKS + 1];
     unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests, [4] task stack overflows
 };
 
@@ -117,9 +121,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                         s_begin = ((P.p.sample_begin - pix) % g + g) % g;
                         s_count = s_begin < P.p.sample_count ? (P.p.sample_count - s_begin + g - 1) / g : 0;
                     }
-                    if (P.chunks > 1) {  // this item's range of the pixel's samples: k in [chunk*n/C, (chunk+1)*n/C)
-                        k = (int)((long long)chunk * s_count / P.chunks);
-                        s_count = (int)((long long)(chunk + 1) * s_count / P.chunks);
+                    if (P.chunks > 1) {  // this item's range of the pixel's samples
+                        k = (int)((long long)P.chunk_cum[chunk] * s_count / P.chunk_total);
+                        s_count = (int)((long long)P.chunk_cum[chunk + 1] * s_count / P.chunk_total);
                     }
                 }
             }
@@ -755,17 +759,36 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
 // One thread owns one (pixel, sample range) work item at a time.  With whole pixels as items (one range) the kernel ends
 // in a tail as long as the most expensive pixel — at 100 spp about 14 ms of 220, during which most of the device idles —
 // and an image with fewer pixels than the device has resident threads (the reference's own 200x100 default is 20 000)
-// never fills it.  So every pixel's samples are cut into `chunks` contiguous ranges of at least four samples; a
-// range's partial sum goes to its own plane and k_sum_chunks adds the planes up in range order (reproducible bit for
-// bit; differs from the one-range sum only by float reassociation, like the multi-GPU split).  Measured on the bench
-// workload: 453 (1 range) / 477 (2) / 490 (4) / 498 (16) Mpaths/s.
-int pick_chunks(const rtnw_render_params& p) {
-    if (const char* e = getenv("RTNW_SAMPLE_CHUNKS")) { const int v = atoi(e); if (v > 0) return std::min(v, 256); }
-    int per_pixel = p.sample_count;  // samples of a pixel in this call (ROTATE: sample_count is the frame's total over sample_stride ranks)
-    if (p.flags & RTNW_F_ROTATE_SAMPLES) per_pixel = p.sample_count / p.sample_stride;
+// never fills it.  So every pixel's samples are cut into contiguous ranges, handed out range-major; a range's partial
+// sum goes to its own plane and k_sum_chunks adds the planes up in range order (reproducible bit for bit; differs from
+// the one-range sum only by float reassociation, like the multi-GPU split).  Ranges are four samples long (more when
+// there are more than ~110 samples per pixel) and the last ones shrink to 4, 2, 1, 1, because the kernel's tail is as long
+// as the longest item still running when the items run out.  Measured on the bench workload: 453 (1 range) / 477 (2) /
+// 490 (4) / 498 (16) Mpaths/s.
+void pick_chunks(const rtnw_render_params& p, render_args& a) {
+    int per_pixel = p.sample_count;  // most samples a pixel has in this call (ROTATE: sample_count is the frame's total over sample_stride ranks)
+    if (p.flags & RTNW_F_ROTATE_SAMPLES) per_pixel = (p.sample_count + p.sample_stride - 1) / p.sample_stride;
     const long long plane_bytes = (long long)p.nx * p.ny * 3 * (long long)sizeof(float);
-    const long long by_memory = std::max<long long>(1, (1ll << 30) / plane_bytes);  // at most 1 GiB of partial sums
-    return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(per_pixel / 4, 32), by_memory));
+    const int by_memory = (int)std::max<long long>(1, std::min<long long>(RTNW_MAX_CHUNKS, (1ll << 30) / plane_bytes));  // <= 1 GiB of partial sums
+    std::vector<int> sizes;
+    int forced = 0;
+    if (const char* e = getenv("RTNW_SAMPLE_CHUNKS")) forced = std::min(atoi(e), RTNW_MAX_CHUNKS);
+    if (forced <= 0) {
+        const int base = std::max(4, (per_pixel + 27) / 28);
+        int rest = per_pixel;
+        while (rest - base >= 8) { sizes.push_back(base); rest -= base; }
+        while (rest > 0) { const int sz = std::max(1, rest / 2); sizes.push_back(sz); rest -= sz; }
+        if ((int)sizes.size() > by_memory) forced = by_memory;
+    }
+    if (forced > 0) {  // equal ranges
+        sizes.clear();
+        const int c = std::max(1, std::min(forced, per_pixel));
+        for (int q = 0; q < c; ++q) sizes.push_back((int)((long long)(q + 1) * per_pixel / c - (long long)q * per_pixel / c));
+    }
+    a.chunks = (int)sizes.size();
+    a.chunk_total = std::max(1, per_pixel);
+    a.chunk_cum[0] = 0;
+    for (int q = 0; q < a.chunks; ++q) a.chunk_cum[q + 1] = a.chunk_cum[q] + sizes[q];
 }
 
 int validate_params(const rtnw_render_params* p) {
@@ -791,7 +814,7 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     a.accum = accum_dev;
     a.ctr = ctx->ctr;
     int rc = RTNW_OK;
-    a.chunks = pick_chunks(a.p);
+    pick_chunks(a.p, a);
     a.chunk_sums = nullptr;
     const size_t plane = (size_t)p->nx * p->ny * 3;
     if (a.chunks > 1) {
