@@ -203,7 +203,7 @@ def main():
 
         def render(**launch):
             st = ds.render_device(cam, launch_params(launch), accum.data_ptr(), stream.cuda_stream)
-            last["rays"] += st.rays; last["kernel_ms"] += st.kernel_ms; last["launches"] += 1
+            last["rays"] += st.rays; last["kernel_ms"] += st.kernel_ms; last["launches"] += st.kernel_launches; last["ranges"] = st.sample_ranges
         mg.render_partitioned(render, accum, ns, dist=dist, dst=0)  # k_render launches of this rank, then one NCCL reduce(sum)
         return last
 
@@ -224,6 +224,7 @@ def main():
         rays += st["rays"]
         kernel_ms.append(st["kernel_ms"])
         launches_per_step = st["launches"]
+        sample_ranges = st["ranges"]
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     clocks = sampler.result()
@@ -314,14 +315,17 @@ def main():
         fp32_peak = ctx.fp32_peak_tflops()  # measured on this device: independent FFMA chains (rtnw_measure_fp32_peak)
         achieved = rays_per_launch * f_ray / kernel_s / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_bytes = nx * ny * 3 * 4 + desc_bytes
+        # scene tables read once + one plane of partial sums per sample range written by k_render, read back and reduced to the
+        # image by k_sum_chunks (0.09 ms of the step)
+        hbm_bytes = desc_bytes + (2 * sample_ranges + 1) * nx * ny * 3 * 4
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "final_northstar 1000x1000x100spp (config 5N: BVH over 1024 floor boxes + "
                                    "translate(rotate_y(BVH over 1000 spheres)) + media + perlin + image texture)",
-                       "paths_per_step": paths_per_step, "partition": f"spp split over {world} GPU(s) (sample ownership rotates with the pixel index), 1 NCCL reduce",
+                       "paths_per_step": paths_per_step, "partition": f"spp split over {world} GPU(s) (sample ownership rotates with the pixel index), 1 NCCL reduce; "
+                                    f"{sample_ranges} sample ranges per pixel per launch",
                        "l2": "flushed between timed steps (256 MiB write)", "traversal": "narrowed" if args.flags & 4 else "reference-exact",
                        "seed": SEED},
             "mrays_per_s": mrays, "rays_per_path": tot_rays.item() / (paths_per_step * args.steps),
@@ -333,10 +337,10 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch of THIS workload (ncu capture of
-                         # `bench.py --steps 1 --warmup 1`, profiles/round1_r12_bench_dram_traffic.csv): the scene tables and the
-                         # image texture are read once; the 12 MB image is still dirty in the 126 MB L2 when the kernel ends,
-                         # so it does not show as DRAM writes
-                         "traffic": 2415360, "kernel": "k_render", "kernel_ms": 1e3 * kernel_s, "flop_per_ray": f_ray,
+                         # `bench.py --steps 1 --warmup 1`, profiles/round1_r14_bench_dram_traffic.csv): 14 MB read (scene tables,
+                         # image texture) + 272 MB written (27 planes of per-sample-range partial sums, 324 MB, less what is
+                         # still dirty in the 126 MB L2 when the kernel ends)
+                         "traffic": 286354688, "kernel": "k_render", "kernel_ms": 1e3 * kernel_s, "flop_per_ray": f_ray,
                          "peak_source": f"measured FFMA microbenchmark on this GPU (nominal {fp32_nominal:.1f} = {info['sm_count']} SM x "
                                         f"128 lanes x 2 x {sm_mhz:.0f} MHz)",
                          "note": "FP32-issue bound, not HBM/tensor: the scene (<2 MB) lives in L1/L2; see the hbm sub-object",

@@ -186,8 +186,8 @@ typedef struct rtnw_stats {
     uint64_t prim_tests;   /* RTNW_F_COUNTERS only */
     float kernel_ms;       /* device time of the render kernel(s), CUDA events */
     float total_ms;        /* including copies done inside the call */
-    int32_t kernel_launches;
-    int32_t pad;
+    int32_t kernel_launches; /* k_render, + k_sum_chunks when the samples of a pixel were cut into more than one range */
+    int32_t sample_ranges;   /* (pixel, sample range) work items per pixel of this call; their partial sums are added in range order */
 } rtnw_stats;
 
 typedef struct rtnw_ray {

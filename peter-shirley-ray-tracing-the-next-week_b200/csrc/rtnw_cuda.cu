@@ -886,6 +886,7 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
         stats->prim_tests = h[3];
         CUDA_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev0, ctx->ev1));
         stats->kernel_launches = a.chunks > 1 ? 2 : 1;
+        stats->sample_ranges = a.chunks;
     }
     return RTNW_OK;
 }
