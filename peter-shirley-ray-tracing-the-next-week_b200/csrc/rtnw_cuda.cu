@@ -18,8 +18,8 @@
 using namespace rtnw_dev;
 
 #ifndef RTNW_BLOCK
-#define RTNW_BLOCK 256
-#endif
+#define RTNW_BLOCK 320      // x 2 blocks per SM at 96 registers: 640 rays in flight per SM (measured against 256 x 2 at 124
+#endif                      // registers, 192 x 3, 288 x 2, 352 x 2, 384 x 2 and 256 x 3 at 80: DESIGN.md §6)
 #ifndef RTNW_MIN_BLOCKS
 #define RTNW_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for
 #endif
@@ -80,12 +80,13 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     bool alive = true, need = true;
     int pix = -1, k = 0, depth = 0, chunk = 0;
     int s_begin = P.p.sample_begin, s_count = P.p.sample_count;  // the samples of the current pixel
-    f3 col = mk3(0.f, 0.f, 0.f), L = col, T = col;
+    f3 col = mk3(0.f, 0.f, 0.f), T = col;
     ray_t wr;
     wr.o = col; wr.d = mk3(1.f, 1.f, 1.f); wr.time = 0.f;
     rng_t g;
     g.begin(k0, k1, 0, 0);
-    unsigned long long n_rays = 0, box_total = 0, prim_total = 0;
+    unsigned n_rays = 0;  // per thread; summed in 64 bits below
+    unsigned long long box_total = 0, prim_total = 0;
     trav_counters cnt;
     cnt.box_tests = 0; cnt.prim_tests = 0;
 
@@ -135,7 +136,6 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             g.begin(k0, k1, (uint32_t)pix, (uint32_t)s);
             camera_ray(P.cam, nx, ny, pix % nx, pix / nx, g, wr);
             depth = 0;
-            L = mk3(0.f, 0.f, 0.f);
             T = mk3(1.f, 1.f, 1.f);
             need = false;
         }
@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
         // ---- one level of color(), PSC/main.cpp:25-46, in iterative form
         if (tracing) {
             ++n_rays;
+            f3 L = mk3(0.f, 0.f, 0.f);  // radiance of this path: only its last ray (a light, or the sky) adds any, so it need not live across rounds
             hit_t h;
             key_to_hit(P.S, key, P.p.t_max, h);
             need = true;
@@ -204,8 +205,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     if (threadIdx.x % RTNW_GROUP == 0 && sm.overflow) atomicAdd(&P.ctr[4], 1ull);
     // work counters: one atomic per warp
     if (COUNT) { box_total = cnt.box_tests; prim_total = cnt.prim_tests; }
-    for (int o = 16; o > 0; o >>= 1) n_rays += __shfl_xor_sync(FULL, n_rays, o);
-    if (lane == 0) atomicAdd(&P.ctr[1], n_rays);
+    unsigned long long rays_total = n_rays;
+    for (int o = 16; o > 0; o >>= 1) rays_total += __shfl_xor_sync(FULL, rays_total, o);
+    if (lane == 0) atomicAdd(&P.ctr[1], rays_total);
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {
             box_total += __shfl_xor_sync(FULL, box_total, o);

@@ -475,11 +475,14 @@ __device__ __forceinline__ void group_sync() {
 #ifndef RTNW_QL_MULT
 #define RTNW_QL_MULT 16
 #endif
+#ifndef RTNW_QL_ABS
+#define RTNW_QL_ABS 4096  // gate ring size (a power of two; 0: RTNW_QL_MULT * GROUP, for power-of-two block sizes)
+#endif
 template <int GROUP>
 struct coop_smem {
     static_assert(GROUP <= 512 && GROUP % 32 == 0, "a task carries its owner slot in 9 bits");
     static constexpr int QN = RTNW_QN_MULT * GROUP;   // node task stack
-    static constexpr int QL = RTNW_QL_MULT * GROUP;   // gate queue (circular, power of two); node work pauses while < 4*GROUP slots are free
+    static constexpr int QL = RTNW_QL_ABS ? RTNW_QL_ABS : RTNW_QL_MULT * GROUP;   // gate queue (circular, power of two); node work pauses while < 4*GROUP slots are free
     static_assert((QL & (QL - 1)) == 0, "the gate ring must be a power of two");
     float4 ray_o[GROUP];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
     float4 ray_d[GROUP];  // d.xyz, w = dot(d,d)
