@@ -337,10 +337,10 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch of THIS workload (ncu capture of
-                         # `bench.py --steps 1 --warmup 1`, profiles/round1_r14_bench_dram_traffic.csv): 14 MB read (scene tables,
-                         # image texture) + 272 MB written (27 planes of per-sample-range partial sums, 324 MB, less what is
+                         # `bench.py --steps 1 --warmup 1`, profiles/round1_r15_bench_dram_traffic.csv): 16 MB read (scene tables,
+                         # image texture) + 284 MB written (27 planes of per-sample-range partial sums, 324 MB, less what is
                          # still dirty in the 126 MB L2 when the kernel ends)
-                         "traffic": 286354688, "kernel": "k_render", "kernel_ms": 1e3 * kernel_s, "flop_per_ray": f_ray,
+                         "traffic": 299885312, "kernel": "k_render", "kernel_ms": 1e3 * kernel_s, "flop_per_ray": f_ray,
                          "peak_source": f"measured FFMA microbenchmark on this GPU (nominal {fp32_nominal:.1f} = {info['sm_count']} SM x "
                                         f"128 lanes x 2 x {sm_mhz:.0f} MHz)",
                          "note": "FP32-issue bound, not HBM/tensor: the scene (<2 MB) lives in L1/L2; see the hbm sub-object",
