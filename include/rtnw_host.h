@@ -38,6 +38,14 @@ int32_t rtnw_host_scene_leaf_count(const rtnw_host_scene* s);
 int rtnw_host_scene_camera(const rtnw_host_scene* s, int32_t nx, int32_t ny, rtnw_camera* cam);
 int rtnw_host_scene_view(const rtnw_host_scene* s, rtnw_host_view* view);
 
+/* Texture ingest, replaces `stbi_load("picture.png", &nx, &ny, &nn, 0)` (PSC/main.cpp:93): decode a non-interlaced PNG
+ * (grey, grey+alpha, RGB, RGBA, palette; 8-bit, or 16-bit keeping the high byte) into tightly packed RGB8, the layout
+ * image_texture::value indexes (PSC/surface_texture.h:19-30).  Alpha is dropped — the reference hands stb's 4-channel
+ * buffer to a 3-channel indexer.  Free with rtnw_host_free_image.  Scene name "earth@<file.png>" builds
+ * earth() (PSC/main.cpp:87-97) with the decoded file as its texture. */
+int rtnw_host_load_png(const char* path, unsigned char** rgb, int32_t* nx, int32_t* ny);
+void rtnw_host_free_image(unsigned char* rgb);
+
 /* camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist, t0, t1), PSC/camera.h:21-39 */
 int rtnw_host_make_camera(const float lookfrom[3], const float lookat[3], const float vup[3], float vfov, float aspect,
                           float aperture, float focus_dist, float t0, float t1, rtnw_camera* cam);

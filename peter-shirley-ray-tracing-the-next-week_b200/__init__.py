@@ -115,7 +115,7 @@ DEVICE_SYMBOLS = ["rtnw_last_error", "rtnw_abi_version", "rtnw_device_count", "r
                   "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays"]
 HOST_SYMBOLS = ["rtnw_host_last_error", "rtnw_host_scene_build", "rtnw_host_scene_free", "rtnw_host_scene_desc",
                 "rtnw_host_scene_leaf_count", "rtnw_host_scene_camera", "rtnw_host_scene_view", "rtnw_host_make_camera",
-                "rtnw_host_quantize", "rtnw_host_write_ppm"]
+                "rtnw_host_quantize", "rtnw_host_write_ppm", "rtnw_host_load_png", "rtnw_host_free_image"]
 
 
 def build_native(device: bool = True, host: bool = True) -> None:
@@ -148,6 +148,9 @@ def host_lib() -> C.CDLL:
                                             C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(Camera)]
         L.rtnw_host_quantize.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.rtnw_host_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.rtnw_host_load_png.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.rtnw_host_free_image.argtypes = [C.POINTER(C.c_ubyte)]
+        L.rtnw_host_free_image.restype = None
         _host = L
     return _host
 
@@ -251,6 +254,17 @@ def quantize(sums: np.ndarray, ns: int, clamp255: bool = True) -> np.ndarray:
     out = np.empty((ny, nx, 3), dtype=np.int32)
     _check_host(host_lib().rtnw_host_quantize(sums.ctypes.data, nx, ny, ns, int(clamp255), out.ctypes.data))
     return out
+
+
+def load_png(path) -> np.ndarray:
+    """Texture ingest (replaces stbi_load, PSC/main.cpp:93): a PNG file as the (ny, nx, 3) uint8 array image_texture indexes."""
+    px = C.POINTER(C.c_ubyte)()
+    nx, ny = C.c_int32(), C.c_int32()
+    _check_host(host_lib().rtnw_host_load_png(str(path).encode(), C.byref(px), C.byref(nx), C.byref(ny)))
+    try:
+        return np.ctypeslib.as_array(px, shape=(ny.value, nx.value, 3)).copy()
+    finally:
+        host_lib().rtnw_host_free_image(px)
 
 
 def write_ppm(path: str, sums: np.ndarray, ns: int, clamp255: bool = True, binary: bool = False) -> None:

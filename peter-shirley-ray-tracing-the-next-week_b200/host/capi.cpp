@@ -15,6 +15,8 @@ struct rtnw_host_scene {
     rtnw_scenes::view view;
 };
 
+namespace rtnw { unsigned char* load_png_rgb8(const char* path, int& nx, int& ny, std::string& err); }
+
 namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) {
@@ -52,6 +54,14 @@ int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
     else if (name == "simple_light") { world = simple_light(); v = view_two_perlin(); v.sky = false; v.emit = true; }
     else if (name == "two_spheres") { world = two_spheres(); v = view_cornell(); v.sky = true; }
     else if (name == "earth") { world = earth(); v = view_cornell(); }
+    else if (name.rfind("earth@", 0) == 0) {  // earth() with its texture decoded from a PNG file, PSC/main.cpp:87-97
+        int tx = 0, ty = 0;
+        std::string err;
+        unsigned char* tex = rtnw::load_png_rgb8(name.c_str() + 6, tx, ty, err);
+        if (!tex) return fail(RTNW_ERR_INVALID, err);
+        world = earth(tex, tx, ty);
+        v = view_cornell();
+    }
     else if (name == "random_scene") { world = random_scene(); v = view_ch01(); v.emit = true; }
     else if (name == "test") { world = test_scene(); v = view_two_perlin(); v.sky = false; v.emit = true; }
     else if (name == "stress_shells") { world = stress_shells(); v = view_ch01(); v.aperture = 0.0f; }
@@ -114,6 +124,17 @@ static inline void quantize_pixel(const float* sum, int32_t ns, int clamp255, in
         out[c] = v;
     }
 }
+
+int rtnw_host_load_png(const char* path, unsigned char** rgb, int32_t* nx, int32_t* ny) {
+    if (!path || !rgb || !nx || !ny) return fail(RTNW_ERR_INVALID, "null argument");
+    int tx = 0, ty = 0;
+    std::string err;
+    unsigned char* px = rtnw::load_png_rgb8(path, tx, ty, err);
+    if (!px) return fail(RTNW_ERR_INVALID, err);
+    *rgb = px; *nx = tx; *ny = ty;
+    return RTNW_OK;
+}
+void rtnw_host_free_image(unsigned char* rgb) { delete[] rgb; }
 
 int rtnw_host_quantize(const float* sums, int32_t nx, int32_t ny, int32_t ns, int32_t clamp255, int32_t* rgb_out) {
     if (!sums || !rgb_out || nx <= 0 || ny <= 0 || ns <= 0) return fail(RTNW_ERR_INVALID, "bad quantize arguments");

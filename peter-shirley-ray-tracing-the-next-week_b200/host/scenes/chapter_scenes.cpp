@@ -202,13 +202,16 @@ unsigned char* synthetic_earth(int& nx, int& ny) {
     return px;
 }
 
-hitable* earth() {
+hitable* earth(unsigned char* tex, int nx, int ny) {
     pool w(2);
     w.add(new xz_rect(63, 483, 55, 482, 554, lamp(7)));
-    int nx, ny;
-    unsigned char* tex = synthetic_earth(nx, ny);
     w.add(new sphere(vec3(360, 250, 150), 100, new lambertian(new image_texture(tex, nx, ny))));
     return w.as_list();
+}
+hitable* earth() {
+    int nx, ny;
+    unsigned char* tex = synthetic_earth(nx, ny);
+    return earth(tex, nx, ny);
 }
 
 hitable* final_northstar() {

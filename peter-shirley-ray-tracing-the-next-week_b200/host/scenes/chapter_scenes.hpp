@@ -32,6 +32,7 @@ hitable* test_scene();             // PSC/main.cpp:135-145
 hitable* simple_light();           // PSC/main.cpp:122-133
 hitable* two_spheres();            // PSC/main.cpp:99-110
 hitable* earth();                  // PSC/main.cpp:87-97 with the synthetic RGB8 image
+hitable* earth(unsigned char* rgb, int nx, int ny);  // ... with a caller-supplied RGB8 image (decoded PNG)
 hitable* stress_shells();          // test fixture (not in the reference): 600 nested shells, every ray passes every box
 hitable* wrap_in_bvh(hitable* flat_list, float t0, float t1);  // `new bvh_node(list->list, list->list_size, t0, t1)`
 
