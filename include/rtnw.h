@@ -238,6 +238,13 @@ int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
 int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam,
                        const rtnw_render_params* params, float* accum_rgb_dev, void* cuda_stream, rtnw_stats* stats);
 
+/* How rtnw_render / rtnw_render_device cut the samples of a pixel into (pixel, sample range) work items for `params`
+ * (host arithmetic only, no device needed).  Writes n+1 cumulative boundaries cum[0..n] (cum[0] = 0, cum[n] = total,
+ * total = the most samples a pixel has in the call) and returns n (<= cap), or a negative status.  Range c of a pixel
+ * with m <= total samples covers its samples k in [cum[c]*m/total, cum[c+1]*m/total): the ranges of every pixel are
+ * disjoint and cover all of its samples; their partial sums are added in range order (rtnw_stats.sample_ranges = n). */
+int rtnw_plan_sample_ranges(const rtnw_render_params* params, int32_t* cum, int32_t cap);
+
 /* Output stage on the device, PSC/main.cpp:315-325: col = sums/ns (vec3::operator/=: multiply by float(1.0/ns)), sqrt gamma,
  * int(255.99*c) in double, optional clamp to 255.  accum_rgb_dev = nx*ny*3 float sums in DEVICE memory (e.g. the buffer
  * rtnw_render_device filled and NCCL reduced); rgb_out = nx*ny*3 int32 in HOST memory, in the reference's output order

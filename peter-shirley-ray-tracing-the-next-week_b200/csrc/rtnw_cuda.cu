@@ -1138,6 +1138,17 @@ int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     return rc;
 }
 
+int rtnw_plan_sample_ranges(const rtnw_render_params* params, int32_t* cum, int32_t cap) {
+    const int rc = validate_params(params);
+    if (rc != RTNW_OK) return rc;
+    if (!cum || cap < 1) return fail(RTNW_ERR_INVALID, "null / empty output");
+    render_args a;
+    pick_chunks(*params, a);
+    if (a.chunks > cap) return fail(RTNW_ERR_INVALID, "cap is smaller than the number of sample ranges");
+    for (int q = 0; q <= a.chunks; ++q) cum[q] = a.chunk_cum[q];
+    return a.chunks;
+}
+
 int rtnw_quantize_device(rtnw_ctx* ctx, const float* accum_rgb_dev, int32_t nx, int32_t ny, int32_t ns, int32_t clamp255, int32_t* rgb_out) {
     int rc = check_ctx(ctx);
     if (rc != RTNW_OK) return rc;
