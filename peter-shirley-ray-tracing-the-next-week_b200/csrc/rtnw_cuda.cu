@@ -49,10 +49,11 @@ struct block_smem { group_smem g[RTNW_BLOCK / RTNW_GROUP]; };
 
 // The sample loop of PSC/main.cpp:299-313 as ONE persistent megakernel.
 //
-// One thread owns one pixel at a time: its samples are traced back to back and summed in sample order, exactly like
-// `col += temp` in the reference, so a pixel's sum never depends on scheduling (no atomics on the image).  A thread
-// that finishes its pixel pulls the next one from a global counter (warp-aggregated atomic); a thread whose path ends
-// starts the next sample of its pixel in the same round (path regeneration, which absorbs the 51-bounce tail).
+// One thread owns one work item at a time — a pixel and a contiguous range of its samples (pick_chunks): the samples
+// are traced back to back and summed in sample order like `col += temp` in the reference; the ranges of a pixel are
+// added up in range order by k_sum_chunks, so a pixel's sum never depends on scheduling (no atomics on the image).  A
+// thread that finishes its item pulls the next one from a global counter (warp-aggregated atomic); a thread whose path
+// ends starts the next sample of its item in the same round (path regeneration, which absorbs the 51-bounce tail).
 //
 // The block advances in rounds, one ray per thread per round: regenerate -> closest hit -> shade.  The closest hit is
 // block-cooperative (coop_closest_hit): list items in lockstep, BVH items as uniform tasks from shared-memory queues.
@@ -77,12 +78,14 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 #ifdef RTNW_ROUND_STATS
     const long long t_start = clock64();
 #endif
-    bool alive = true, need = true;
-    int pix = -1, k = 0, depth = 0, chunk = 0;
-    int s_begin = P.p.sample_begin, s_count = P.p.sample_count;  // the samples of the current pixel
-    f3 col = mk3(0.f, 0.f, 0.f), T = col;
+    // The work item of a thread (pixel, sample range, running sum) lives in shared memory: it is touched when a path
+    // ends, i.e. once every few rounds, and would otherwise occupy eight registers across every round.
+    const int me = threadIdx.x % RTNW_GROUP;
+    bool alive = true, need = true, has_item = false;
+    int depth = 0;
+    f3 T = mk3(0.f, 0.f, 0.f);
     ray_t wr;
-    wr.o = col; wr.d = mk3(1.f, 1.f, 1.f); wr.time = 0.f;
+    wr.o = T; wr.d = mk3(1.f, 1.f, 1.f); wr.time = 0.f;
     rng_t g;
     g.begin(k0, k1, 0, 0);
     unsigned n_rays = 0;  // per thread; summed in 64 bits below
@@ -92,18 +95,22 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 
     for (;;) {
         // ---- next sample of the pixel, or next pixel, PSC/main.cpp:299-308
-        if (alive && need && pix >= 0 && k == s_count) {
-            if (P.chunks > 1) {  // partial sum of one sample range; k_sum_chunks adds the ranges up in order
-                float* dst = P.chunk_sums + 3ull * ((unsigned long long)chunk * (unsigned long long)(nx * ny) + (unsigned long long)pix);
-                dst[0] = col.x; dst[1] = col.y; dst[2] = col.z;
-            } else {
-                float* dst = P.accum + 3ull * (unsigned long long)pix;
-                if (accumulate) { dst[0] += col.x; dst[1] += col.y; dst[2] += col.z; }
-                else { dst[0] = col.x; dst[1] = col.y; dst[2] = col.z; }
+        if (alive && need && has_item) {
+            const float4 acc = sm.acc[me];
+            if (__float_as_int(acc.w) == sm.span[me].y) {  // k == end of the range: the item is finished
+                const int4 it = sm.span[me];  // z = pixel, w = sample range
+                if (P.chunks > 1) {  // partial sum of one sample range; k_sum_chunks adds the ranges up in order
+                    float* dst = P.chunk_sums + 3ull * ((unsigned long long)it.w * (unsigned long long)(nx * ny) + (unsigned long long)it.z);
+                    dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z;
+                } else {
+                    float* dst = P.accum + 3ull * (unsigned long long)it.z;
+                    if (accumulate) { dst[0] += acc.x; dst[1] += acc.y; dst[2] += acc.z; }
+                    else { dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; }
+                }
+                has_item = false;
             }
-            pix = -1;
         }
-        const bool want = alive && need && pix < 0;
+        const bool want = alive && need && !has_item;
         const unsigned m = __ballot_sync(FULL, want);
         if (m) {
             const int leader = __ffs(m) - 1;
@@ -114,9 +121,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                 const unsigned long long mine = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
                 if (mine >= npix * (unsigned long long)P.chunks) alive = false;
                 else {
-                    chunk = (int)(mine / npix);  // work item = (sample range, pixel), range-major
-                    pix = P.p.pixel_begin + (int)(mine % npix) * P.p.pixel_stride; k = 0; col = mk3(0.f, 0.f, 0.f);
-                    s_count = P.p.sample_count;
+                    const int chunk = (int)(mine / npix);  // work item = (sample range, pixel), range-major
+                    const int pix = P.p.pixel_begin + (int)(mine % npix) * P.p.pixel_stride;
+                    int k = 0, s_begin = P.p.sample_begin, s_count = P.p.sample_count;
                     if (rotate) {  // RTNW_F_ROTATE_SAMPLES: ownership of the samples rotates with the pixel index
                         const int g = P.p.sample_stride;
                         s_begin = ((P.p.sample_begin - pix) % g + g) % g;
@@ -126,22 +133,30 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                         k = (int)((long long)P.chunk_cum[chunk] * s_count / P.chunk_total);
                         s_count = (int)((long long)P.chunk_cum[chunk + 1] * s_count / P.chunk_total);
                     }
+                    sm.acc[me] = make_float4(0.f, 0.f, 0.f, __int_as_float(k));
+                    sm.span[me] = make_int4(s_begin, s_count, pix, chunk);
+                    has_item = true;
                 }
             }
         }
         if (RTNW_GROUP == 32 ? __ballot_sync(FULL, alive) == 0 : __syncthreads_count(alive) == 0) break;  // the group is done
-        if (alive && need && k < s_count) {
-            const int s = s_begin + k * P.p.sample_stride;
-            ++k;
-            g.begin(k0, k1, (uint32_t)pix, (uint32_t)s);
-            camera_ray(P.cam, nx, ny, pix % nx, pix / nx, g, wr);
-            depth = 0;
-            T = mk3(1.f, 1.f, 1.f);
-            need = false;
+        if (alive && need && has_item) {
+            const int k = __float_as_int(sm.acc[me].w);
+            const int4 sp = sm.span[me];
+            if (k < sp.y) {
+                const int pix = sp.z;
+                const int s = sp.x + k * P.p.sample_stride;
+                sm.acc[me].w = __int_as_float(k + 1);
+                g.begin(k0, k1, (uint32_t)pix, (uint32_t)s);
+                camera_ray(P.cam, nx, ny, pix % nx, pix / nx, g, wr);
+                depth = 0;
+                T = mk3(1.f, 1.f, 1.f);
+                need = false;
+            }
         }
         // ---- world->hit(r, t_min, t_max, rec), PSC/main.cpp:27
         medium_key mk;
-        mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)pix; mk.sample = g.sample; mk.depth = (uint32_t)depth;
+        mk.k0 = k0; mk.k1 = k1; mk.pixel = (uint32_t)sm.span[me].z; mk.sample = g.sample; mk.depth = (uint32_t)depth;
         const bool tracing = alive && !need;  // a pixel that owns no sample of this call has no ray (RTNW_F_ROTATE_SAMPLES, ns < G)
 #ifdef RTNW_ROUND_STATS
         const long long c0 = clock64();
@@ -191,7 +206,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                     if (!(L.y == L.y)) L.y = 0.f;
                     if (!(L.z == L.z)) L.z = 0.f;
                 }
-                col = col + L;
+                float4 acc = sm.acc[me];  // col += de_nan(color(...)), PSC/main.cpp:311-312
+                acc.x += L.x; acc.y += L.y; acc.z += L.z;
+                sm.acc[me] = acc;
             }
         }
 #ifdef RTNW_ROUND_STATS

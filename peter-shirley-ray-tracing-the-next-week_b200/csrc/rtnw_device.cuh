@@ -488,6 +488,9 @@ struct coop_smem {
     float4 ray_d[GROUP];  // d.xyz, w = dot(d,d)
     float4 ray_i[GROUP];  // 1/d, w = time
     uint4 mkey[GROUP];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
+    float4 acc[GROUP];    // k_render: the owner's work item — xyz = sum of its finished samples, w = next sample index k (int bits)
+    int4 span[GROUP];     // k_render: the owner's work item — x = first sample of its pixel in this call (s_begin), y = end index of
+                          // its range, z = pixel, w = range
     hkey_t key[GROUP];
     uint32_t q[QN + QL];  // [0, QN): node task stack; [QN, QN + QL): gate ring (one array: a push is a single predicated store)
     int n[2];             // node stack height, double-buffered across rounds
