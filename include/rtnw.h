@@ -225,6 +225,14 @@ int rtnw_ctx_info(rtnw_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t*
 int rtnw_measure_fp32_peak(rtnw_ctx* ctx, float* tflops);
 
 int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out);
+
+/* The device tables rtnw_scene_upload derives from `desc`, built on the host WITHOUT a device and copied out for
+ * inspection (the invariants the traversal's exactness rests on are checked on the CPU from these, tests/test_device_tables.py).
+ * table: 0 = record stream (32 B each: 8 floats, [6] = tag bits, [7] = int), 1 = per-record leaf id (int32),
+ * 2 = gates (2 x int32: first records of the one or two leaves, -1 = none), 3 = gate tree (128 B per 4-wide node:
+ * minx[4] miny[4] minz[4] maxx[4] maxy[4] maxz[4] ref[4] pad[4]; ref >= 0 wide node, < 0 ~gate, INT32_MIN absent).
+ * Copies min(cap_bytes, size) bytes into buf (may be NULL) and returns the table's size in bytes, or a negative status. */
+int64_t rtnw_scene_inspect(const rtnw_scene_desc* desc, int32_t table, void* buf, size_t cap_bytes);
 int rtnw_scene_free(rtnw_ctx* ctx, rtnw_scene* scene);
 
 /* Replaces PSC/main.cpp:304-313 over all pixels.  accum_rgb (host, nx*ny*3 floats, index (j*nx+i)*3+c with the

@@ -112,7 +112,7 @@ assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 48
 # every symbol include/rtnw.h and include/rtnw_host.h declare (tests check the libraries export all of them)
 DEVICE_SYMBOLS = ["rtnw_last_error", "rtnw_abi_version", "rtnw_device_count", "rtnw_ctx_create", "rtnw_ctx_destroy",
                   "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_quantize_device", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
-                  "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays", "rtnw_plan_sample_ranges"]
+                  "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays", "rtnw_plan_sample_ranges", "rtnw_scene_inspect"]
 HOST_SYMBOLS = ["rtnw_host_last_error", "rtnw_host_scene_build", "rtnw_host_scene_free", "rtnw_host_scene_desc",
                 "rtnw_host_scene_leaf_count", "rtnw_host_scene_camera", "rtnw_host_scene_view", "rtnw_host_make_camera",
                 "rtnw_host_quantize", "rtnw_host_write_ppm", "rtnw_host_load_png", "rtnw_host_free_image"]
@@ -171,6 +171,8 @@ def device_lib() -> C.CDLL:
         L.rtnw_measure_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.rtnw_quantize_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.rtnw_plan_sample_ranges.argtypes = [C.POINTER(RenderParams), C.POINTER(C.c_int32), C.c_int32]
+        L.rtnw_scene_inspect.argtypes = [C.POINTER(SceneDesc), C.c_int32, C.c_void_p, C.c_size_t]
+        L.rtnw_scene_inspect.restype = C.c_int64
         L.rtnw_scene_upload.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
         L.rtnw_scene_free.argtypes = [C.c_void_p, C.c_void_p]
         L.rtnw_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]
@@ -272,6 +274,20 @@ def write_ppm(path: str, sums: np.ndarray, ns: int, clamp255: bool = True, binar
     ny, nx, _ = sums.shape
     sums = np.ascontiguousarray(sums, dtype=np.float32)
     _check_host(host_lib().rtnw_host_write_ppm(str(path).encode(), sums.ctypes.data, nx, ny, ns, int(clamp255), int(binary)))
+
+
+def device_tables(desc_ptr) -> dict:
+    """The tables rtnw_scene_upload derives from a scene_desc, built on the host (no GPU needed): record stream, leaf ids,
+    gates and the 4-wide gate tree (include/rtnw.h: rtnw_scene_inspect)."""
+    out = {}
+    for table, (name, dtype, width) in enumerate([("recs", np.float32, 8), ("rec_leaf", np.int32, 1), ("gates", np.int32, 2),
+                                                    ("wnodes", np.float32, 32)]):
+        n = device_lib().rtnw_scene_inspect(desc_ptr, table, None, 0)
+        _check_dev(min(n, 0))
+        a = np.empty(n // np.dtype(dtype).itemsize, dtype=dtype)
+        device_lib().rtnw_scene_inspect(desc_ptr, table, a.ctypes.data, a.nbytes)
+        out[name] = a.reshape(-1, width) if width > 1 else a
+    return out
 
 
 def plan_sample_ranges(params) -> np.ndarray:

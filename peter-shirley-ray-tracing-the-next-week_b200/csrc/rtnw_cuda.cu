@@ -1004,6 +1004,23 @@ int rtnw_measure_fp32_peak(rtnw_ctx* ctx, float* tflops) {
     return RTNW_OK;
 }
 
+int64_t rtnw_scene_inspect(const rtnw_scene_desc* desc, int32_t table, void* buf, size_t cap_bytes) {
+    if (!desc) return fail(RTNW_ERR_INVALID, "null scene_desc");
+    stream_builder sb(*desc);
+    if (!sb.run()) return fail(RTNW_ERR_INVALID, "scene_desc: " + sb.err);
+    const void* src = nullptr;
+    size_t bytes = 0;
+    switch (table) {
+        case 0: src = sb.recs.data(); bytes = sb.recs.size() * sizeof(rec); break;
+        case 1: src = sb.leaf.data(); bytes = sb.leaf.size() * sizeof(int32_t); break;
+        case 2: src = sb.gate_leaves.data(); bytes = sb.gate_leaves.size() * sizeof(int2); break;
+        case 3: src = sb.wnodes.data(); bytes = sb.wnodes.size() * sizeof(float4); break;
+        default: return fail(RTNW_ERR_INVALID, "unknown table");
+    }
+    if (buf && cap_bytes) std::memcpy(buf, src, std::min(cap_bytes, bytes));
+    return (int64_t)bytes;
+}
+
 int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out) {
     if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
     *out = nullptr;
