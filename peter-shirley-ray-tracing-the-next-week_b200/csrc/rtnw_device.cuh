@@ -470,7 +470,7 @@ __device__ __forceinline__ void group_sync() {
     if (GROUP == 32) __syncwarp(); else __syncthreads();
 }
 #ifndef RTNW_QN_MULT
-#define RTNW_QN_MULT 16
+#define RTNW_QN_MULT 12
 #endif
 #ifndef RTNW_QL_MULT
 #define RTNW_QL_MULT 16
