@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RTNW_ABI_VERSION 4
+#define RTNW_ABI_VERSION 5
 
 enum rtnw_status {
     RTNW_OK = 0,
@@ -176,7 +176,10 @@ typedef struct rtnw_render_params {
     /* pixel subset of this call: pixels p = pixel_begin + k*pixel_stride, k in [0, pixel_count); p = j*nx + i.
      * pixel_count == 0 means every pixel (begin 0, stride 1).  Pixels outside the subset are left untouched.  Used by
      * the multi-GPU split for the samples that do not divide evenly among the ranks. */
-    int32_t pixel_begin, pixel_stride, pixel_count, pad;
+    int32_t pixel_begin, pixel_stride, pixel_count;
+    /* 0 = the library's schedule (rtnw_plan_sample_ranges); N > 0 = cut every pixel's samples into N equal ranges (1 = one
+     * work item per pixel).  Only the float summation order depends on it. */
+    int32_t sample_ranges;
 } rtnw_render_params;
 
 typedef struct rtnw_stats {
@@ -186,8 +189,8 @@ typedef struct rtnw_stats {
     uint64_t prim_tests;   /* RTNW_F_COUNTERS only */
     float kernel_ms;       /* device time of the render kernel(s), CUDA events */
     float total_ms;        /* including copies done inside the call */
-    int32_t kernel_launches; /* k_render, + k_sum_chunks when the samples of a pixel were cut into more than one range */
-    int32_t sample_ranges;   /* (pixel, sample range) work items per pixel of this call; their partial sums are added in range order */
+    int32_t kernel_launches; /* k_render, + k_finish_fixed when the samples of a pixel were cut into more than one range */
+    int32_t sample_ranges;   /* (pixel, sample range) work items per pixel of this call; their partial sums are added in 64-bit fixed point (order independent) */
 } rtnw_stats;
 
 typedef struct rtnw_ray {
@@ -242,7 +245,9 @@ int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
                 float* accum_rgb, rtnw_stats* stats);
 
 /* Same, but accum_rgb_dev is DEVICE memory owned by the caller (e.g. a torch tensor that is then reduced with
- * NCCL); the buffer is overwritten.  cuda_stream may be NULL (ctx stream).  Synchronous on return. */
+ * NCCL); the buffer is overwritten.  The call is STREAM-ORDERED on cuda_stream (a cudaStream_t): work queued there before the
+ * call (fills, a previous reduce) completes first.  NULL = the CUDA legacy default stream, which is torch's default stream.
+ * Synchronous on return. */
 int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam,
                        const rtnw_render_params* params, float* accum_rgb_dev, void* cuda_stream, rtnw_stats* stats);
 
@@ -250,7 +255,7 @@ int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera
  * (host arithmetic only, no device needed).  Writes n+1 cumulative boundaries cum[0..n] (cum[0] = 0, cum[n] = total,
  * total = the most samples a pixel has in the call) and returns n (<= cap), or a negative status.  Range c of a pixel
  * with m <= total samples covers its samples k in [cum[c]*m/total, cum[c+1]*m/total): the ranges of every pixel are
- * disjoint and cover all of its samples; their partial sums are added in range order (rtnw_stats.sample_ranges = n). */
+ * disjoint and cover all of its samples; their partial sums are added exactly, in 64-bit fixed point (rtnw_stats.sample_ranges = n). */
 int rtnw_plan_sample_ranges(const rtnw_render_params* params, int32_t* cum, int32_t cap);
 
 /* Output stage on the device, PSC/main.cpp:315-325: col = sums/ns (vec3::operator/=: multiply by float(1.0/ns)), sqrt gamma,

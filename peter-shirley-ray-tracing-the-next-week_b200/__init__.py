@@ -21,7 +21,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 LIB_DIR = PKG_DIR / "lib"
 
-RTNW_ABI_VERSION = 4
+RTNW_ABI_VERSION = 5
 RTNW_OK = 0
 RTNW_ERR_INVALID, RTNW_ERR_CUDA, RTNW_ERR_UNSUPPORTED, RTNW_ERR_NOMEM = -1, -2, -3, -4
 BG_BLACK, BG_SKY = 0, 1
@@ -90,7 +90,7 @@ class RenderParams(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("sample_begin", C.c_int32), ("sample_count", C.c_int32),
                 ("sample_stride", C.c_int32), ("max_depth", C.c_int32), ("t_min", C.c_float), ("t_max", C.c_float),
                 ("background", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64),
-                ("pixel_begin", C.c_int32), ("pixel_stride", C.c_int32), ("pixel_count", C.c_int32), ("pad", C.c_int32)]
+                ("pixel_begin", C.c_int32), ("pixel_stride", C.c_int32), ("pixel_count", C.c_int32), ("sample_ranges", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -224,11 +224,11 @@ class HostScene:
         return cam
 
     def params(self, nx=None, ny=None, ns=None, seed=1, sample_begin=0, sample_stride=1, flags_extra=0, pixel_begin=0,
-               pixel_stride=1, pixel_count=0) -> RenderParams:
+               pixel_stride=1, pixel_count=0, sample_ranges=0) -> RenderParams:
         v = self.view
         return RenderParams(v.nx if nx is None else nx, v.ny if ny is None else ny, sample_begin, v.ns if ns is None else ns,
                             sample_stride, 50, v.t_min, FLT_MAX, v.background, v.flags | flags_extra, seed, pixel_begin,
-                            pixel_stride, pixel_count, 0)
+                            pixel_stride, pixel_count, sample_ranges)
 
     def close(self):
         if self._h:

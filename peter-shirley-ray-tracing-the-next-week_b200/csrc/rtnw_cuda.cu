@@ -37,12 +37,31 @@ struct render_args {
     rtnw_camera cam;
     rtnw_render_params p;
     float* accum;                 // nx*ny*3 sums, index (j*nx+i)*3+c
-    float* chunk_sums;            // chunks > 1: chunks * nx*ny*3 partial sums, summed in chunk order by k_sum_chunks
+    unsigned long long* fixed;    // chunks > 1: nx*ny*3 fixed-point sums (add_fixed / k_finish_fixed), all zero between renders
     int chunks;                   // each pixel's samples are cut into this many contiguous ranges, one work item each
     int chunk_total;              // range c of a pixel with n samples: k in [cum[c]*n/total, cum[c+1]*n/total)
     int chunk_cum[RTNW_MAX_CHUNKS + 1];
     unsigned long long* ctr;      // [0] next pixel, [1] rays, [2] box tests, [3] primitive tests, [4] task stack overflows
 };
+
+// Partial sums of the sample ranges of a pixel are added in 64-bit fixed point with integer atomics: integer addition
+// commutes, so the pixel's sum is the same bits whatever order the ranges finish in, with ONE plane of scratch instead of
+// one float plane per range.  Value = round(v * 2^41), always even; bit 0 is a sticky "not a number" flag (a NaN or infinite
+// partial sum — only possible without RTNW_F_DE_NAN — makes the pixel NaN, as `col += temp` does in the reference).
+// Resolution 4.5e-13, range +-2^22 (larger partial sums saturate; radiance sums are < 1e5).
+__device__ __forceinline__ void add_fixed(unsigned long long* dst, float v) {
+    if (v - v == 0.f) {  // finite
+        const float c = fminf(fmaxf(v, -4194303.f), 4194303.f);
+        const long long q = __double2ll_rn((double)c * 1099511627776.0) << 1;  // 2^40, then << 1
+        if (q != 0) atomicAdd(dst, (unsigned long long)q);
+    } else {
+        atomicOr(dst, 1ull);
+    }
+}
+__device__ __forceinline__ float from_fixed(unsigned long long u) {
+    if (u & 1ull) return __int_as_float(0x7fc00000);
+    return (float)((double)(long long)u * (1.0 / 2199023255552.0));  // 2^-41, one rounding
+}
 
 typedef coop_smem<RTNW_GROUP> group_smem;
 struct block_smem { group_smem g[RTNW_BLOCK / RTNW_GROUP]; };
@@ -50,8 +69,8 @@ struct block_smem { group_smem g[RTNW_BLOCK / RTNW_GROUP]; };
 // The sample loop of PSC/main.cpp:299-313 as ONE persistent megakernel.
 //
 // One thread owns one work item at a time — a pixel and a contiguous range of its samples (pick_chunks): the samples
-// are traced back to back and summed in sample order like `col += temp` in the reference; the ranges of a pixel are
-// added up in range order by k_sum_chunks, so a pixel's sum never depends on scheduling (no atomics on the image).  A
+// are traced back to back and summed in sample order like `col += temp` in the reference; the partial sums of a pixel's
+// ranges are added in 64-bit fixed point (add_fixed: integer atomics commute, so a pixel's sum never depends on scheduling).  A
 // thread that finishes its item pulls the next one from a global counter (warp-aggregated atomic); a thread whose path
 // ends starts the next sample of its item in the same round (path regeneration, which absorbs the 51-bounce tail).
 //
@@ -74,7 +93,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
     const bool sky = P.p.background == RTNW_BG_SKY;
 
-    if (threadIdx.x % RTNW_GROUP == 0) sm.overflow = 0;
+    coop_init<RTNW_GROUP>(sm);
+    group_sync<RTNW_GROUP>();
+    int r3 = 0;  // index of the cooperative traversal's next round, mod 3 (coop_bvh_item)
 #ifdef RTNW_ROUND_STATS
     const long long t_start = clock64();
 #endif
@@ -99,9 +120,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
             const float4 acc = sm.acc[me];
             if (__float_as_int(acc.w) == sm.span[me].y) {  // k == end of the range: the item is finished
                 const int4 it = sm.span[me];  // z = pixel, w = sample range
-                if (P.chunks > 1) {  // partial sum of one sample range; k_sum_chunks adds the ranges up in order
-                    float* dst = P.chunk_sums + 3ull * ((unsigned long long)it.w * (unsigned long long)(nx * ny) + (unsigned long long)it.z);
-                    dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z;
+                if (P.chunks > 1) {  // partial sum of one sample range
+                    unsigned long long* dst = P.fixed + 3ull * (unsigned long long)it.z;
+                    add_fixed(dst, acc.x); add_fixed(dst + 1, acc.y); add_fixed(dst + 2, acc.z);
                 } else {
                     float* dst = P.accum + 3ull * (unsigned long long)it.z;
                     if (accumulate) { dst[0] += acc.x; dst[1] += acc.y; dst[2] += acc.z; }
@@ -161,7 +182,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 #ifdef RTNW_ROUND_STATS
         const long long c0 = clock64();
 #endif
-        const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt);
+        const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt, r3);
 #ifdef RTNW_ROUND_STATS
         if (threadIdx.x == 0) { RTNW_STAT(10, 1); RTNW_STAT(11, clock64() - c0); }
         const long long c1 = clock64();
@@ -253,8 +274,10 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     mk.k0 = (uint32_t)seed; mk.k1 = (uint32_t)(seed >> 32); mk.pixel = in.key; mk.sample = 0; mk.depth = 0;
     trav_counters cnt;
     cnt.box_tests = 0; cnt.prim_tests = 0;
-    if (threadIdx.x % RTNW_GROUP == 0) sm.overflow = 0;
-    const hkey_t key = coop_closest_hit<RTNW_GROUP, false>(S, sm, r, active, t_min, t_max, mk, cnt);
+    coop_init<RTNW_GROUP>(sm);
+    group_sync<RTNW_GROUP>();
+    int r3 = 0;
+    const hkey_t key = coop_closest_hit<RTNW_GROUP, false>(S, sm, r, active, t_min, t_max, mk, cnt, r3);
     if (!active) return;
     hit_t h;
     key_to_hit(S, key, t_max, h);
@@ -291,17 +314,17 @@ __global__ void k_quantize(const float* __restrict__ sums, int nx, int ny, float
     }
 }
 
-// chunks > 1: a pixel's sum = its sample ranges' partial sums added in range order (deterministic; differs from the
-// single-range sum only by float reassociation, like the multi-GPU split)
-__global__ void k_sum_chunks(const float* __restrict__ parts, int chunks, unsigned long long plane, int pixel_begin, int pixel_stride,
-                             int pixel_count, int accumulate, float* __restrict__ accum) {
+// chunks > 1: the fixed-point sums of the subset's pixels become float sums (added to accum with RTNW_F_ACCUMULATE) and the
+// plane is cleared for the next render
+__global__ void k_finish_fixed(unsigned long long* __restrict__ fixed, int pixel_begin, int pixel_stride, int pixel_count,
+                               int accumulate, float* __restrict__ accum) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= pixel_count) return;
     const unsigned long long at = 3ull * (unsigned long long)(pixel_begin + q * pixel_stride);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float v = parts[at + c];
-        for (int r = 1; r < chunks; ++r) v += parts[(unsigned long long)r * plane + at + c];
+        const float v = from_fixed(fixed[at + c]);
+        fixed[at + c] = 0ull;
         if (accumulate) accum[at + c] += v; else accum[at + c] = v;
     }
 }
@@ -418,8 +441,8 @@ struct rtnw_ctx {
     int sm_count = 0, clock_khz = 0, smem_optin = 0, l2_bytes = 0;
     float* accum = nullptr;          // device accumulation buffer of rtnw_render
     size_t accum_floats = 0;
-    float* chunk_sums = nullptr;     // partial sums of the sample-range split (small images)
-    size_t chunk_floats = 0;
+    unsigned long long* fixed = nullptr;  // fixed-point plane of the sample-range split (zero between renders)
+    size_t fixed_words = 0;
     unsigned long long* ctr = nullptr;  // 4 device counters
     int blocks_per_sm[2] = {0, 0};
     // freed scene slabs are kept for the next upload (cudaMalloc/cudaFree synchronise the device and can take
@@ -478,7 +501,7 @@ struct stream_builder {
     // Append the records of prim slots [first, first+count).  first_cont: narrowing flag of the first primitive;
     // the following primitives of the range always continue its scope (list semantics).
     bool emit_prims(int32_t first, int32_t count, bool first_cont, bool boundary) {
-        if (first < 0 || count < 0 || first + count > d.n_prim_slots) return bad("primitive range out of bounds");
+        if (first < 0 || count < 0 || count > d.n_prim_slots - first) return bad("primitive range out of bounds");
         bool cont = first_cont;
         size_t last_head = (size_t)-1;  // the record a leaf scan tests last (a moving sphere / medium head, not its trailing records)
         for (int32_t s = first; s < first + count; ++s) {
@@ -664,6 +687,9 @@ struct stream_builder {
         }
         for (int a = 0; a < 6; ++a) wnodes[8 * me + a] = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
         wnodes[8 * me + 6] = make_float4(bits(ref[0]), bits(ref[1]), bits(ref[2]), bits(ref[3]));
+        int32_t lrec[4];  // gate children: first record of the gate's first leaf (prefetch hint), else -1
+        for (int q = 0; q < 4; ++q) lrec[q] = (ref[q] != RTNW_REF_NONE && ref[q] < 0) ? gate_leaves[~ref[q]].x : -1;
+        wnodes[8 * me + 7] = make_float4(bits(lrec[0]), bits(lrec[1]), bits(lrec[2]), bits(lrec[3]));
         return (int)me;
     }
     // one BVH item: returns the root wide node and the depth of its gate tree
@@ -769,7 +795,9 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
     const long long warps_needed = ((long long)a.p.pixel_count * a.chunks + 31) / 32;
     const long long blocks_needed = (warps_needed * 32 + RTNW_BLOCK - 1) / RTNW_BLOCK;
     if (blocks_needed < blocks) blocks = (int)blocks_needed;
+#ifdef RTNW_TUNING  // A/B builds only (scripts/ab_build.sh): the product library reads no environment on the launch path
     if (const char* e = getenv("RTNW_GRID_BLOCKS")) { const int v = atoi(e); if (v > 0) blocks = v; }
+#endif
     k_render<COUNT><<<blocks, RTNW_BLOCK, sizeof(block_smem), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RTNW_OK;
@@ -779,28 +807,25 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
 // in a tail as long as the most expensive pixel — at 100 spp about 14 ms of 220, during which most of the device idles —
 // and an image with fewer pixels than the device has resident threads (the reference's own 200x100 default is 20 000)
 // never fills it.  So every pixel's samples are cut into contiguous ranges, handed out range-major; a range's partial
-// sum goes to its own plane and k_sum_chunks adds the planes up in range order (reproducible bit for bit; differs from
-// the one-range sum only by float reassociation, like the multi-GPU split).  Ranges are four samples long (more when
+// sum is added to the pixel's 64-bit fixed-point sum (add_fixed) and k_finish_fixed turns the plane into floats
+// (reproducible bit for bit; differs from the one-range float sum only by rounding).  Ranges are four samples long (more when
 // there are more than ~110 samples per pixel) and the last ones shrink to 4, 2, 1, 1, because the kernel's tail is as long
 // as the longest item still running when the items run out.  Measured on the bench workload: 453 (1 range) / 477 (2) /
 // 490 (4) / 498 (16) Mpaths/s.
 void pick_chunks(const rtnw_render_params& p, render_args& a) {
     int per_pixel = p.sample_count;  // most samples a pixel has in this call (ROTATE: sample_count is the frame's total over sample_stride ranks)
     if (p.flags & RTNW_F_ROTATE_SAMPLES) per_pixel = (p.sample_count + p.sample_stride - 1) / p.sample_stride;
-    const long long plane_bytes = (long long)p.nx * p.ny * 3 * (long long)sizeof(float);
-    const int by_memory = (int)std::max<long long>(1, std::min<long long>(RTNW_MAX_CHUNKS, (1ll << 30) / plane_bytes));  // <= 1 GiB of partial sums
     std::vector<int> sizes;
-    int forced = 0;
+    int forced = std::min(p.sample_ranges, RTNW_MAX_CHUNKS);  // rtnw_render_params.sample_ranges: 0 = the schedule below
+#ifdef RTNW_TUNING  // A/B builds only
     if (const char* e = getenv("RTNW_SAMPLE_CHUNKS")) forced = std::min(atoi(e), RTNW_MAX_CHUNKS);
+#endif
     if (forced <= 0) {
         const int base = std::max(4, (per_pixel + 27) / 28);
         int rest = per_pixel;
         while (rest - base >= 8) { sizes.push_back(base); rest -= base; }
         while (rest > 0) { const int sz = std::max(1, rest / 2); sizes.push_back(sz); rest -= sz; }
-        if ((int)sizes.size() > by_memory) forced = by_memory;
-    }
-    if (forced > 0) {  // equal ranges
-        sizes.clear();
+    } else {  // equal ranges
         const int c = std::max(1, std::min(forced, per_pixel));
         for (int q = 0; q < c; ++q) sizes.push_back((int)((long long)(q + 1) * per_pixel / c - (long long)q * per_pixel / c));
     }
@@ -816,6 +841,7 @@ int validate_params(const rtnw_render_params* p) {
     if (p->sample_count <= 0 || p->sample_stride <= 0 || p->sample_begin < 0) return fail(RTNW_ERR_INVALID, "bad sample range");
     if (p->max_depth < 0) return fail(RTNW_ERR_INVALID, "bad max_depth");
     if (p->background > RTNW_BG_SKY) return fail(RTNW_ERR_INVALID, "bad background");
+    if (p->sample_ranges < 0) return fail(RTNW_ERR_INVALID, "bad sample_ranges");
     if (p->pixel_count < 0 || (p->pixel_count > 0 && (p->pixel_begin < 0 || p->pixel_stride < 1 ||
         (long long)p->pixel_begin + (long long)(p->pixel_count - 1) * p->pixel_stride >= (long long)p->nx * p->ny)))
         return fail(RTNW_ERR_INVALID, "bad pixel subset");
@@ -834,29 +860,30 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     a.ctr = ctx->ctr;
     int rc = RTNW_OK;
     pick_chunks(a.p, a);
-    a.chunk_sums = nullptr;
+    a.fixed = nullptr;
     const size_t plane = (size_t)p->nx * p->ny * 3;
     if (a.chunks > 1) {
-        if (ctx->chunk_floats < plane * a.chunks) {
+        if (ctx->fixed_words < plane) {
             CUDA_TRY(cudaStreamSynchronize(st));
-            if (ctx->chunk_sums) cudaFree(ctx->chunk_sums);
-            ctx->chunk_sums = nullptr;
-            ctx->chunk_floats = 0;
-            if (cudaMalloc(&ctx->chunk_sums, plane * a.chunks * sizeof(float)) != cudaSuccess) {
+            if (ctx->fixed) cudaFree(ctx->fixed);
+            ctx->fixed = nullptr;
+            ctx->fixed_words = 0;
+            if (cudaMalloc(&ctx->fixed, plane * sizeof(unsigned long long)) != cudaSuccess) {
                 cudaGetLastError();
-                return fail(RTNW_ERR_NOMEM, "cudaMalloc of the sample-range partial sums failed");
+                return fail(RTNW_ERR_NOMEM, "cudaMalloc of the sample-range accumulation plane failed");
             }
-            ctx->chunk_floats = plane * a.chunks;
+            ctx->fixed_words = plane;
+            CUDA_TRY(cudaMemsetAsync(ctx->fixed, 0, plane * sizeof(unsigned long long), st));  // k_finish_fixed keeps it zero afterwards
         }
-        a.chunk_sums = ctx->chunk_sums;
+        a.fixed = ctx->fixed;
     }
     CUDA_TRY(cudaMemsetAsync(ctx->ctr, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(ctx->ev0, st));
     rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true>(ctx, a, st) : launch_render<false>(ctx, a, st);
     if (rc != RTNW_OK) return rc;
     if (a.chunks > 1) {
-        k_sum_chunks<<<(a.p.pixel_count + 255) / 256, 256, 0, st>>>(a.chunk_sums, a.chunks, (unsigned long long)plane, a.p.pixel_begin,
-                                                                   a.p.pixel_stride, a.p.pixel_count, (p->flags & RTNW_F_ACCUMULATE) ? 1 : 0, accum_dev);
+        k_finish_fixed<<<(a.p.pixel_count + 255) / 256, 256, 0, st>>>(a.fixed, a.p.pixel_begin, a.p.pixel_stride, a.p.pixel_count,
+                                                                      (p->flags & RTNW_F_ACCUMULATE) ? 1 : 0, accum_dev);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(ctx->ev1, st));
@@ -947,7 +974,9 @@ int rtnw_ctx_create(int device, rtnw_ctx** out) {
     cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&c->l2_bytes, cudaDevAttrL2CacheSize, device);
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    // a BLOCKING stream: ordered with the legacy default stream (torch's default), so a caller's fills / reduces on stream 0
+    // and the library's own launches cannot overtake each other
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaMalloc(&c->ctr, 8 * sizeof(unsigned long long));
@@ -963,7 +992,7 @@ int rtnw_ctx_destroy(rtnw_ctx* c) {
     if (!c) return RTNW_OK;
     cudaSetDevice(c->device);
     if (c->accum) cudaFree(c->accum);
-    if (c->chunk_sums) cudaFree(c->chunk_sums);
+    if (c->fixed) cudaFree(c->fixed);
     for (int q = 0; q < 2; ++q) if (c->spare_slab[q]) cudaFree(c->spare_slab[q]);
     if (c->ctr) cudaFree(c->ctr);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1132,7 +1161,7 @@ int rtnw_render_device(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera
     if (rc != RTNW_OK) return rc;
     if (!scene || !cam || !accum_rgb_dev) return fail(RTNW_ERR_INVALID, "null argument");
     if ((rc = validate_params(params)) != RTNW_OK) return rc;
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : cudaStreamLegacy;  // NULL = the legacy default stream
     return render_core(ctx, scene, cam, params, accum_rgb_dev, st, stats);
 }
 

@@ -465,6 +465,10 @@ __device__ unsigned long long g_round_stats[32];
 // The cooperating GROUP is a template parameter: a whole block (group_sync = __syncthreads) or a single warp
 // (group_sync = __syncwarp: no block barrier anywhere, every warp of the SM progresses independently; with 32 lanes the
 // round policy below degenerates to "node rounds until the stack is empty, then 32-wide gate rounds").
+#ifndef RTNW_PREFETCH
+#define RTNW_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <int GROUP>
 __device__ __forceinline__ void group_sync() {
     if (GROUP == 32) __syncwarp(); else __syncthreads();
@@ -493,9 +497,9 @@ struct coop_smem {
                           // its range, z = pixel, w = range
     hkey_t key[GROUP];
     uint32_t q[QN + QL];  // [0, QN): node task stack; [QN, QN + QL): gate ring (one array: a push is a single predicated store)
-    int n[2];             // node stack height, double-buffered across rounds
-    unsigned lh[2];       // gate queue head (consumed), double-buffered; counts up, index = value % QL
-    unsigned lt;          // gate queue tail (produced)
+    int n[3];             // node stack height, one buffer per round (read r % 3, popped/pushed (r + 1) % 3, cleared (r + 2) % 3)
+    unsigned lh[3];       // gate queue head (consumed), same rotation; counts up for the whole kernel, index = value % QL
+    unsigned lt;          // gate queue tail (produced); never reset
     int overflow;         // a push did not fit (cannot happen for validated scenes); reported to the host
 };
 // task = owner slot (9 bits) | wide node index or gate index (23 bits)
@@ -503,6 +507,14 @@ struct coop_smem {
 #define RTNW_TASK(slot, idx) (((uint32_t)(slot) << RTNW_IDX_BITS) | (uint32_t)(idx))
 #define RTNW_TASK_SLOT(task) ((int)((task) >> RTNW_IDX_BITS))
 #define RTNW_TASK_IDX(task) ((task) & ((1u << RTNW_IDX_BITS) - 1u))
+
+// once per kernel, before the first closest-hit query (followed by a group_sync)
+template <int GROUP>
+__device__ __forceinline__ void coop_init(coop_smem<GROUP>& sm) {
+    const int tid = threadIdx.x % GROUP;
+    if (tid < 3) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
+    if (tid == 3) { sm.lt = 0u; sm.overflow = 0; }
+}
 
 // Closest hit of the block's rays against the BVH item whose gate tree has root `root`.  Owners have already written
 // their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
@@ -513,7 +525,7 @@ struct coop_smem {
 // drain the gate queue.
 template <int GROUP, bool COUNT>
 __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GROUP>& sm, int root, int tree_depth, bool active,
-                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt) {
+                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt, int& r3) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int QN = coop_smem<GROUP>::QN, QL = coop_smem<GROUP>::QL;
     const int tid = threadIdx.x % GROUP;  // index within the cooperating group
@@ -521,23 +533,28 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
 #ifdef RTNW_ROUND_STATS
     int stat_busy = 0; long long stat_c = 0; const long long stat_c0 = clock64();
 #endif
-    if (tid < 2) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
-    if (tid == 2) sm.lt = 0u;
-    group_sync<GROUP>();
+    // The rounds of ALL items of a kernel form one sequence r = 0, 1, 2, ... (r3 = r % 3 lives in a register of every
+    // thread).  Round r reads n[r3] / lh[r3], writes the popped state to buffer r3 + 1 and clears n[r3 + 2] — the buffer
+    // the round before it read, which nobody looks at any more.  An item ends in a round that finds both queues empty;
+    // the next item's root tasks then go to n[r3 + 1], cleared one round earlier, so entering an item needs no reset and no
+    // barrier of its own: a thread still reading n[r3] / lh[r3] / lt of the final round never sees them change.
+    if (tid == 0) sm.lh[r3] = sm.lt;  // empty ring; lh[r3] was last read three rounds ago
     {   // one task per ray: the root of the gate tree
         const unsigned b = __ballot_sync(FULL, active);
         int base = 0;
-        if (lane == 0 && b) base = atomicAdd(&sm.n[0], __popc(b));
+        if (lane == 0 && b) base = atomicAdd(&sm.n[r3], __popc(b));
         base = __shfl_sync(FULL, base, 0);
         if (active) sm.q[base + __popc(b & lt_mask)] = RTNW_TASK(tid, root);
     }
     group_sync<GROUP>();
 #pragma unroll 1
-    for (int round = 0;; ++round) {
-        const int n = sm.n[round & 1];
-        const unsigned lh = sm.lh[round & 1], ltail = sm.lt;
+    for (;;) {
+        const int nxt = r3 == 2 ? 0 : r3 + 1, prv = r3 == 0 ? 2 : r3 - 1;
+        const int n = sm.n[r3];
+        const unsigned lh = sm.lh[r3], ltail = sm.lt;
         const int queued = (int)(ltail - lh);
-        if (n == 0 && queued == 0) break;
+        if (tid == 0) sm.n[prv] = 0;
+        if (n == 0 && queued == 0) { r3 = nxt; break; }
         // node tasks this round: none while the gate ring is nearly full; otherwise as many as the stack has room for
         const int room = (QN - n - 3 * tree_depth) / 3;
         const int take = (queued > QL - 4 * GROUP) ? 0 : min(min(n, GROUP), max(room, 1));
@@ -547,7 +564,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
         uint32_t task = 0;
         if (tid < take) task = sm.q[base + tid];
         else if (tid >= node_threads && tid - node_threads < 2 * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> 1)) & (QL - 1))];
-        if (tid == 0) { sm.n[(round + 1) & 1] = base; sm.lh[(round + 1) & 1] = lh + (unsigned)drain; }  // pop both
+        if (tid == 0) { sm.n[nxt] = base; sm.lh[nxt] = lh + (unsigned)drain; }  // pop both
 #ifdef RTNW_ROUND_STATS
         if (tid == 0) {
             RTNW_STAT(0, 1); RTNW_STAT(1, take); RTNW_STAT(2, drain); RTNW_STAT(8, n); RTNW_STAT(9, queued);
@@ -576,6 +593,26 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             pass[2] = live & (ref[2] != RTNW_REF_NONE) & hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, ro.w);
             pass[3] = live & (ref[3] != RTNW_REF_NONE) & hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, ro.w);
             if (COUNT && live) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
+#if RTNW_PREFETCH
+            {   // the children that passed are popped a round (>= 1000 cycles) from now: pull their lines into L1 off the critical path
+#if RTNW_PREFETCH >= 2
+                const float4 lf = __ldg(N + 7);  // first record of each gate child's first leaf
+                const int lrec[4] = {__float_as_int(lf.x), __float_as_int(lf.y), __float_as_int(lf.z), __float_as_int(lf.w)};
+#endif
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (pass[j]) {
+                        if (ref[j] >= 0) prefetch_l1(S.wnodes + 8 * (size_t)ref[j]);
+                        else {
+                            prefetch_l1(S.gates + (~ref[j]));
+#if RTNW_PREFETCH >= 2
+                            prefetch_l1(S.recs + lrec[j]);
+#endif
+                        }
+                    }
+                }
+            }
+#endif
             // warp-aggregated appends: wide nodes back onto the stack, gates to the gate ring
             unsigned bn[4], bl[4];
             int tn = 0, tl = 0;
@@ -588,7 +625,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             int base_n = 0;
             unsigned base_l = 0;
             if (lane == 0) {
-                if (tn) base_n = atomicAdd(&sm.n[(round + 1) & 1], tn);
+                if (tn) base_n = atomicAdd(&sm.n[nxt], tn);
                 if (tl) base_l = atomicAdd(&sm.lt, (unsigned)tl);
             }
             base_n = __shfl_sync(FULL, base_n, 0);
@@ -623,6 +660,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
         }
         group_sync<GROUP>();
+        r3 = nxt;
 #ifdef RTNW_ROUND_STATS
         if (tid == 0) { const long long d = clock64() - stat_c; RTNW_STAT(stat_busy <= 64 ? 15 : stat_busy <= 128 ? 16 : stat_busy <= 192 ? 17 : 18, d); }
 #endif
@@ -636,7 +674,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
 // thread without a ray passes active = false and still works on the other threads' BVH tasks.
 template <int GROUP, bool COUNT>
 __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_smem<GROUP>& sm, const ray_t& wr, bool active,
-                                                   float t_min, float t_max, const medium_key& mk, trav_counters& cnt) {
+                                                   float t_min, float t_max, const medium_key& mk, trav_counters& cnt, int& r3) {
     const int tid = threadIdx.x % GROUP;
     sm.key[tid] = RTNW_KEY_NONE;
     sm.mkey[tid] = make_uint4(mk.pixel, mk.sample, mk.depth, 0u);
@@ -655,7 +693,7 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
             sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
             sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
             sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-            coop_bvh_item<GROUP, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt);
+            coop_bvh_item<GROUP, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
         } else if (active) {
             float lim = best_t;
 #pragma unroll 1

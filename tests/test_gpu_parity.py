@@ -357,35 +357,55 @@ def test_rotated_sample_split_is_an_even_partition(rtnw, ctx, ns, world):
     ds.close()
 
 
-def test_small_image_sample_ranges(rtnw, ctx, monkeypatch):
-    """A pixel with enough samples is rendered as several (sample range, pixel) work items
-    whose partial sums are added in range order: same paths, same rays, the sums equal up to float reassociation, and
-    still bitwise reproducible.  RTNW_SAMPLE_CHUNKS forces the number of ranges (1 = one thread per pixel)."""
+def test_small_image_sample_ranges(rtnw, ctx):
+    """A pixel with enough samples is rendered as several (sample range, pixel) work items whose partial sums are added
+    in 64-bit fixed point: same paths, same rays, the sums equal up to float rounding, and still bitwise reproducible.
+    rtnw_render_params.sample_ranges forces the number of ranges (1 = one thread per pixel)."""
     import torch
     hs = rtnw.HostScene("cornell_smoke")
     ds = ctx.upload(hs.desc_ptr)
     nx, ny, ns = 64, 48, 37
     cam = hs.camera(nx, ny)
-    monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", "1")
-    one, s1 = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4))
+    one, s1 = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4, sample_ranges=1))
     assert s1.kernel_launches == 1
-    for forced in (None, "5", "64"):
-        if forced is None:
-            monkeypatch.delenv("RTNW_SAMPLE_CHUNKS")
-        else:
-            monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", forced)
-        a, sa = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4))
-        b, sb = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4))
+    for forced in (0, 5, 64):
+        a, sa = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4, sample_ranges=forced))
+        b, sb = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4, sample_ranges=forced))
         assert sa.kernel_launches == 2 and sa.paths == s1.paths and sa.rays == s1.rays == sb.rays
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
         assert np.allclose(a, one, rtol=1e-5, atol=1e-6)
     # with the multi-GPU split and accumulation on top
-    monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", "3")
     acc = torch.zeros((ny, nx, 3), dtype=torch.float32, device="cuda")
     for g in range(2):
-        ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4, sample_begin=g, sample_stride=2,
+        ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=4, sample_begin=g, sample_stride=2, sample_ranges=3,
                                         flags_extra=rtnw.F_ROTATE_SAMPLES | rtnw.F_ACCUMULATE), acc.data_ptr())
     assert np.allclose(acc.cpu().numpy(), one, rtol=1e-5, atol=1e-6)
+    ds.close()
+
+
+def test_fixed_point_range_sums_keep_nan_and_pixel_subsets(rtnw, ctx):
+    """the fixed-point plane: a NaN sample (no de_nan) makes its pixel NaN as `col += temp` does; pixels outside a subset
+    stay untouched; the plane is clean again for the next render"""
+    import torch
+    hs = rtnw.HostScene("ch01_random")  # dielectrics, de_nan off in this chapter's view
+    ds = ctx.upload(hs.desc_ptr)
+    nx, ny, ns = 96, 48, 64
+    cam = hs.camera(nx, ny)
+    one, _ = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=11, sample_ranges=1))
+    many, _ = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=11))
+    assert np.array_equal(np.isnan(one), np.isnan(many))
+    ok = ~np.isnan(one)
+    assert np.allclose(many[ok], one[ok], rtol=1e-5, atol=1e-6)
+    acc = torch.full((ny, nx, 3), -7.0, dtype=torch.float32, device="cuda")
+    ds.render_device(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=11, pixel_begin=5, pixel_stride=3, pixel_count=400), acc.data_ptr())
+    sub = acc.cpu().numpy().reshape(-1, 3)
+    idx = 5 + 3 * np.arange(400)
+    mask = np.zeros(nx * ny, bool); mask[idx] = True
+    assert np.all(sub[~mask] == -7.0)
+    ref = many.reshape(-1, 3)[idx]
+    assert np.array_equal(np.nan_to_num(sub[idx], nan=-1).view(np.uint32), np.nan_to_num(ref, nan=-1).view(np.uint32))
+    again, _ = ds.render(cam, hs.params(nx=nx, ny=ny, ns=ns, seed=11))
+    assert np.array_equal(np.nan_to_num(again, nan=-1).view(np.uint32), np.nan_to_num(many, nan=-1).view(np.uint32))
     ds.close()
 
 

@@ -13,8 +13,8 @@ sys.path.insert(0, str(ROOT))
 rtnw = importlib.import_module("peter-shirley-ray-tracing-the-next-week_b200")
 
 
-def _params(nx, ny, ns, begin=0, stride=1, flags=0):
-    return rtnw.RenderParams(nx, ny, begin, ns, stride, 50, 0.001, rtnw.FLT_MAX, 0, flags, 1, 0, 1, 0, 0)
+def _params(nx, ny, ns, begin=0, stride=1, flags=0, ranges=0):
+    return rtnw.RenderParams(nx, ny, begin, ns, stride, 50, 0.001, rtnw.FLT_MAX, 0, flags, 1, 0, 1, 0, ranges)
 
 
 def _pixel_sample_count(p, pix):
@@ -26,8 +26,7 @@ def _pixel_sample_count(p, pix):
 
 
 @pytest.mark.parametrize("ns", [1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 16, 37, 100, 101, 256, 1000, 5000])
-def test_ranges_partition_every_pixels_samples(ns, monkeypatch):
-    monkeypatch.delenv("RTNW_SAMPLE_CHUNKS", raising=False)
+def test_ranges_partition_every_pixels_samples(ns):
     p = _params(200, 100, ns)
     cum = rtnw.plan_sample_ranges(p)
     n = len(cum) - 1
@@ -42,9 +41,8 @@ def test_ranges_partition_every_pixels_samples(ns, monkeypatch):
 
 
 @pytest.mark.parametrize("ns,world", [(100, 8), (12, 8), (7, 3), (3, 8), (64, 2)])
-def test_rotated_split_ranges_cover_each_ranks_samples(ns, world, monkeypatch):
+def test_rotated_split_ranges_cover_each_ranks_samples(ns, world):
     """multi-GPU: rank g owns, for pixel p, the samples s = (g - p) mod G + k*G below ns; its ranges partition them"""
-    monkeypatch.delenv("RTNW_SAMPLE_CHUNKS", raising=False)
     seen = {}
     for g in range(world):
         p = _params(40, 30, ns, begin=g, stride=world, flags=rtnw.F_ROTATE_SAMPLES)
@@ -65,16 +63,16 @@ def test_rotated_split_ranges_cover_each_ranks_samples(ns, world, monkeypatch):
     assert len(seen) == len(range(0, 40 * 30, 7)) * ns  # every (pixel, sample) exactly once over the ranks
 
 
-def test_forced_count_memory_cap_and_errors(monkeypatch):
-    monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", "5")
-    cum = rtnw.plan_sample_ranges(_params(64, 48, 37))
+def test_forced_count_and_errors():
+    """rtnw_render_params.sample_ranges forces N equal ranges; the schedule no longer depends on the image size (one
+    fixed-point plane whatever the number of ranges)"""
+    cum = rtnw.plan_sample_ranges(_params(64, 48, 37, ranges=5))
     assert len(cum) == 6 and cum[-1] == 37 and np.diff(cum).min() >= 7
-    monkeypatch.setenv("RTNW_SAMPLE_CHUNKS", "1")
-    assert list(rtnw.plan_sample_ranges(_params(64, 48, 37))) == [0, 37]
-    monkeypatch.delenv("RTNW_SAMPLE_CHUNKS")
-    big = rtnw.plan_sample_ranges(_params(8192, 8192, 100))  # 805 MB per plane: at most 1 GiB of partial sums
-    assert len(big) - 1 == 1
-    mid = rtnw.plan_sample_ranges(_params(4096, 2048, 100))  # 100 MB per plane -> 10 planes
-    assert len(mid) - 1 == 10 and mid[-1] == 100
+    assert list(rtnw.plan_sample_ranges(_params(64, 48, 37, ranges=1))) == [0, 37]
+    assert len(rtnw.plan_sample_ranges(_params(64, 48, 37, ranges=1000))) - 1 == 37  # capped by the sample count (and 64)
+    big, small = rtnw.plan_sample_ranges(_params(8192, 8192, 100)), rtnw.plan_sample_ranges(_params(64, 48, 100))
+    assert np.array_equal(big, small) and big[-1] == 100
     with pytest.raises(rtnw.RtnwError):
         rtnw.plan_sample_ranges(_params(64, 48, 0))
+    with pytest.raises(rtnw.RtnwError):
+        rtnw.plan_sample_ranges(_params(64, 48, 8, ranges=-1))
