@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="rtnw", choices=["rtnw", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--flags", type=int, default=0, help="extra RTNW_F_* render flags (4 = narrowed BVH culling)")
+    ap.add_argument("--flags", type=int, default=0, help="extra RTNW_F_* render flags (4 = RTNW_F_FAST_BVH, the non-reference-exact fast traversal mode)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)
@@ -326,7 +326,7 @@ def main():
                                    "translate(rotate_y(BVH over 1000 spheres)) + media + perlin + image texture)",
                        "paths_per_step": paths_per_step, "partition": f"spp split over {world} GPU(s) (sample ownership rotates with the pixel index), 1 NCCL reduce; "
                                     f"{sample_ranges} sample ranges per pixel per launch",
-                       "l2": "flushed between timed steps (256 MiB write)", "traversal": "narrowed" if args.flags & 4 else "reference-exact",
+                       "l2": "flushed between timed steps (256 MiB write)", "traversal": "fast (RTNW_F_FAST_BVH)" if args.flags & 4 else "reference-exact",
                        "seed": SEED},
             "mrays_per_s": mrays, "rays_per_path": tot_rays.item() / (paths_per_step * args.steps),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": desc_bytes * world,

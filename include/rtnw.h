@@ -153,8 +153,10 @@ enum rtnw_background { RTNW_BG_BLACK = 0 /* PSC/main.cpp:44 */, RTNW_BG_SKY = 1 
 /* render flags */
 #define RTNW_F_DE_NAN        1u  /* per-sample NaN->0, PSC/main.cpp:232-242,311 */
 #define RTNW_F_EMIT          2u  /* add material emitted(), PSC/main.cpp:33 (off only for the Ch01/Ch03 snapshots) */
-#define RTNW_F_CULL_NARROW   4u  /* reserved (accepted and ignored): the cooperative BVH traversal always tests exactly the nodes
-                                    and leaves the reference's un-narrowed bvh_node::hit tests */
+#define RTNW_F_FAST_BVH      4u  /* fast traversal mode (default off = reference-exact): BVH boxes and leaves are tested against the
+                                    ray's closest hit so far instead of the un-narrowed range bvh_node::hit hands down (PSC/bvh.h:34-35).
+                                    Fewer box / primitive tests; the closest hit is the same except among candidates whose t is equal
+                                    or within rounding of each other, where another of them may win */
 #define RTNW_F_COUNTERS      8u  /* fill the optional work counters in rtnw_stats */
 #define RTNW_F_ACCUMULATE   16u  /* add this call's pixel sums to accum_rgb instead of overwriting (rtnw_render_device only) */
 #define RTNW_F_ROTATE_SAMPLES 32u /* multi-GPU split that is even for any ns: sample_count is the TOTAL number of samples ns of
@@ -266,7 +268,7 @@ int rtnw_quantize_device(rtnw_ctx* ctx, const float* accum_rgb_dev, int32_t nx, 
                          int32_t* rgb_out);
 
 /* Deterministic closest-hit query: one `world->hit(r, t_min, t_max, rec)` per ray (PSC/main.cpp:27).  Host buffers.
- * flags: reserved.  Media draw their free-flight number from Philox(seed; medium leaf id, depth 0, sample 0, pixel = ray.key),
+ * flags: RTNW_F_FAST_BVH or 0.  Media draw their free-flight number from Philox(seed; medium leaf id, depth 0, sample 0, pixel = ray.key),
  * so results do not depend on traversal order. */
 int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, size_t n, float t_min, float t_max,
                uint32_t flags, uint64_t seed, rtnw_hit* out);
@@ -286,6 +288,30 @@ int rtnw_scatter(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays_in
  * ij = n x 2 int32 {i, j}; sample s = sample index; rays_out[n]. Draw order as in rtnw_render. */
 int rtnw_camera_rays(rtnw_ctx* ctx, const rtnw_camera* cam, int32_t nx, int32_t ny, const int32_t* ij,
                      const int32_t* sample, size_t n, uint64_t seed, rtnw_ray* rays_out);
+
+/* camera::get_ray(s, t) itself (PSC/camera.h:41-47) for n pairs: st = n x 2 floats {s, t}.  The lens-disk and shutter-time
+ * draws of pair q come from the path stream (seed, pixel slot key_base + q, sample 0).  Serves the drop-in `camera::get_ray`. */
+int rtnw_camera_get_rays(rtnw_ctx* ctx, const rtnw_camera* cam, const float* st, size_t n, uint64_t seed, uint32_t key_base,
+                         rtnw_ray* rays_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * N GPUs of one box behind one handle, driven by one host thread (one context + stream per device).  The frame's samples
+ * are split over the devices (device g of G renders, for pixel p, the samples s = (g - p) mod G + k*G: even for any ns),
+ * each device sums into its own buffer, and device 0 adds the buffers in rank order — reading its peers' memory directly
+ * over NVLink where peer access exists, through a staging copy otherwise — before the one device->host copy of the frame.
+ * The same device id may be listed more than once (two contexts on one GPU; used by the single-GPU tests).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rtnw_multi rtnw_multi;
+typedef struct rtnw_multi_scene rtnw_multi_scene;
+int rtnw_ctx_create_multi(const int* device_ids, int n, rtnw_multi** out);   /* n <= 16 */
+int rtnw_ctx_destroy_multi(rtnw_multi* m);
+int rtnw_multi_device_count(const rtnw_multi* m);
+int rtnw_scene_upload_multi(rtnw_multi* m, const rtnw_scene_desc* desc, rtnw_multi_scene** out);   /* to every device */
+int rtnw_scene_free_multi(rtnw_multi* m, rtnw_multi_scene* scene);
+/* Like rtnw_render (host buffer of per-pixel sums, whole frames only: sample_begin 0, sample_stride 1, no pixel subset).
+ * stats: paths / rays / tests summed over the devices, kernel_ms = the slowest device, total_ms = launch to frame on the host. */
+int rtnw_render_multi(rtnw_multi* m, const rtnw_multi_scene* scene, const rtnw_camera* cam, const rtnw_render_params* params,
+                      float* accum_rgb, rtnw_stats* stats);
 
 #ifdef __cplusplus
 }

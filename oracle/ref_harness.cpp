@@ -553,6 +553,24 @@ void ref_render(ref_scene* S, const float* lookfrom, const float* lookat, float 
     }
 }
 
+// The epilogue of the sample loop, PSC/main.cpp:315-325, compiled from the reference's OWN lines: oracle/Makefile cuts
+// main.cpp:315-320 (mean, sqrt gamma, int(255.99*c)) and :322-325 (clamp to 255) into the two include files below (and
+// checks their text), so this function is the reference's arithmetic on a buffer of sums.  out = nx*ny*3 ints, top row first.
+void ref_epilogue(const float* sums, int nx, int ny, int ns, int clamp255, int* out) {
+    size_t o = 0;
+    for (int j = ny - 1; j >= 0; j--) {
+        for (int i = 0; i < nx; i++) {
+            const float* src = sums + 3 * ((size_t)j * nx + i);
+            vec3 col(src[0], src[1], src[2]);
+#include "ref_epilogue_a.inc"
+            if (clamp255) {
+#include "ref_epilogue_b.inc"
+            }
+            out[o++] = ir; out[o++] = ig; out[o++] = ib;
+        }
+    }
+}
+
 // camera::get_ray with the jitter of PSC/main.cpp:305-306, for n (i, j, s) triples
 void ref_camera_rays(const float* lookfrom, const float* lookat, float vfov, float aperture, float focus_dist, float time0,
                      float time1, int nx, int ny, const int* ij, const int* sample, size_t n, uint64_t seed, rtnw_ray* out) {

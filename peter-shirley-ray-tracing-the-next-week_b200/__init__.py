@@ -25,7 +25,7 @@ RTNW_ABI_VERSION = 5
 RTNW_OK = 0
 RTNW_ERR_INVALID, RTNW_ERR_CUDA, RTNW_ERR_UNSUPPORTED, RTNW_ERR_NOMEM = -1, -2, -3, -4
 BG_BLACK, BG_SKY = 0, 1
-F_DE_NAN, F_EMIT, F_CULL_NARROW, F_COUNTERS, F_ACCUMULATE, F_ROTATE_SAMPLES = 1, 2, 4, 8, 16, 32
+F_DE_NAN, F_EMIT, F_FAST_BVH, F_COUNTERS, F_ACCUMULATE, F_ROTATE_SAMPLES = 1, 2, 4, 8, 16, 32
 FLT_MAX = float(np.finfo(np.float32).max)
 
 
@@ -112,7 +112,9 @@ assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 48
 # every symbol include/rtnw.h and include/rtnw_host.h declare (tests check the libraries export all of them)
 DEVICE_SYMBOLS = ["rtnw_last_error", "rtnw_abi_version", "rtnw_device_count", "rtnw_ctx_create", "rtnw_ctx_destroy",
                   "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_quantize_device", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
-                  "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays", "rtnw_plan_sample_ranges", "rtnw_scene_inspect"]
+                  "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays", "rtnw_camera_get_rays", "rtnw_plan_sample_ranges",
+                  "rtnw_scene_inspect", "rtnw_ctx_create_multi", "rtnw_ctx_destroy_multi", "rtnw_multi_device_count",
+                  "rtnw_scene_upload_multi", "rtnw_scene_free_multi", "rtnw_render_multi"]
 HOST_SYMBOLS = ["rtnw_host_last_error", "rtnw_host_scene_build", "rtnw_host_scene_free", "rtnw_host_scene_desc",
                 "rtnw_host_scene_leaf_count", "rtnw_host_scene_camera", "rtnw_host_scene_view", "rtnw_host_make_camera",
                 "rtnw_host_quantize", "rtnw_host_write_ppm", "rtnw_host_load_png", "rtnw_host_free_image"]
@@ -186,6 +188,13 @@ def device_lib() -> C.CDLL:
                                    C.c_void_p, C.c_void_p, C.c_void_p]
         L.rtnw_camera_rays.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
                                        C.c_uint64, C.c_void_p]
+        L.rtnw_camera_get_rays.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.rtnw_ctx_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.rtnw_ctx_destroy_multi.argtypes = [C.c_void_p]
+        L.rtnw_multi_device_count.argtypes = [C.c_void_p]
+        L.rtnw_scene_upload_multi.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+        L.rtnw_scene_free_multi.argtypes = [C.c_void_p, C.c_void_p]
+        L.rtnw_render_multi.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]
         _dev = L
     return _dev
 
@@ -408,12 +417,71 @@ class DeviceScene:
         return sc, att, em, flag
 
 
+class MultiContext:
+    """N GPUs of one box behind one handle (rtnw_ctx_create_multi): spp split + one sum on device 0, in one process."""
+
+    def __init__(self, devices):
+        devices = list(devices)
+        self._h = C.c_void_p()
+        _check_dev(device_lib().rtnw_ctx_create_multi((C.c_int * len(devices))(*devices), len(devices), C.byref(self._h)))
+        self.devices = devices
+
+    def upload(self, desc) -> "MultiScene":
+        return MultiScene(self, desc)
+
+    def close(self):
+        if self._h:
+            device_lib().rtnw_ctx_destroy_multi(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiScene:
+    def __init__(self, mctx: MultiContext, desc):
+        self.mctx = mctx
+        self._h = C.c_void_p()
+        ptr = desc if isinstance(desc, C.POINTER(SceneDesc)) else C.pointer(desc)
+        _check_dev(device_lib().rtnw_scene_upload_multi(mctx._h, ptr, C.byref(self._h)))
+
+    def render(self, cam: Camera, params: RenderParams, out: np.ndarray | None = None):
+        if out is None:
+            out = np.empty((params.ny, params.nx, 3), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == params.nx * params.ny * 3
+        st = Stats()
+        _check_dev(device_lib().rtnw_render_multi(self.mctx._h, self._h, C.byref(cam), C.byref(params), out.ctypes.data, C.byref(st)))
+        return out, st
+
+    def close(self):
+        if self._h and self.mctx._h:
+            device_lib().rtnw_scene_free_multi(self.mctx._h, self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def camera_rays(ctx: Context, cam: Camera, nx: int, ny: int, ij: np.ndarray, sample: np.ndarray, seed: int = 1) -> np.ndarray:
     ij = np.ascontiguousarray(ij, dtype=np.int32).reshape(-1, 2)
     sample = np.ascontiguousarray(sample, dtype=np.int32)
     out = np.zeros(ij.shape[0], dtype=RAY_DTYPE)
     _check_dev(device_lib().rtnw_camera_rays(ctx._h, C.byref(cam), nx, ny, ij.ctypes.data, sample.ctypes.data, ij.shape[0], seed,
                                              out.ctypes.data))
+    return out
+
+
+def camera_get_rays(ctx: Context, cam: Camera, st: np.ndarray, seed: int = 1, key_base: int = 0) -> np.ndarray:
+    """camera::get_ray(s, t) for n pairs (PSC/camera.h:41-47); draws from the path stream (seed, key_base + q, 0)"""
+    st = np.ascontiguousarray(st, dtype=np.float32).reshape(-1, 2)
+    out = np.zeros(st.shape[0], dtype=RAY_DTYPE)
+    _check_dev(device_lib().rtnw_camera_get_rays(ctx._h, C.byref(cam), st.ctypes.data, st.shape[0], seed, key_base, out.ctypes.data))
     return out
 
 

@@ -30,6 +30,7 @@ static_assert(RTNW_GROUP == RTNW_BLOCK || RTNW_GROUP == 32,
               "cooperating group = the whole block (__syncthreads) or one warp (__syncwarp); other sizes would need named barriers");
 
 #define RTNW_MAX_CHUNKS 64
+#define RTNW_MAX_DEVICES 16
 
 // ================================================================================================ kernels
 struct render_args {
@@ -78,7 +79,7 @@ struct block_smem { group_smem g[RTNW_BLOCK / RTNW_GROUP]; };
 // block-cooperative (coop_closest_hit): list items in lockstep, BVH items as uniform tasks from shared-memory queues.
 // A per-lane traversal state machine was measured at 2-13 active lanes of 32 per instruction (profiles/r1-r3*.txt);
 // this form keeps every phase uniform across the warp.
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const render_args P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     group_smem& sm = reinterpret_cast<block_smem*>(smem_raw)->g[threadIdx.x / RTNW_GROUP];
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 #ifdef RTNW_ROUND_STATS
         const long long c0 = clock64();
 #endif
-        const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt, r3);
+        const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT, FAST>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt, r3);
 #ifdef RTNW_ROUND_STATS
         if (threadIdx.x == 0) { RTNW_STAT(10, 1); RTNW_STAT(11, clock64() - c0); }
         const long long c1 = clock64();
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 }
 
 // one world->hit() per ray, PSC/main.cpp:27 — the same block-cooperative closest hit the renderer uses
+template <bool FAST>
 __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const rtnw_ray* __restrict__ rays, size_t n, float t_min,
                                                       float t_max, uint64_t seed, rtnw_hit* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     coop_init<RTNW_GROUP>(sm);
     group_sync<RTNW_GROUP>();
     int r3 = 0;
-    const hkey_t key = coop_closest_hit<RTNW_GROUP, false>(S, sm, r, active, t_min, t_max, mk, cnt, r3);
+    const hkey_t key = coop_closest_hit<RTNW_GROUP, false, FAST>(S, sm, r, active, t_min, t_max, mk, cnt, r3);
     if (!active) return;
     hit_t h;
     key_to_hit(S, key, t_max, h);
@@ -308,7 +310,10 @@ __global__ void k_quantize(const float* __restrict__ sums, int nx, int ny, float
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float col = sqrtf(src[c] * inv_ns);      // col /= float(ns) multiplies by k = float(1.0/ns), PSC/vec3.h:134-141
-        int v = (int)(255.99 * (double)col);            // int(255.99*col[c]): the product is a double
+        const double x = 255.99 * (double)col;          // int(255.99*col[c]): the product is a double
+        // out of int range or NaN (a NaN sum without de_nan): x86's cvttsd2si, which the reference binary executes, returns
+        // INT_MIN; CUDA's conversion would saturate / give 0
+        int v = (x > -2147483649.0 && x < 2147483648.0) ? (int)x : (int)0x80000000;
         if (clamp255 && v > 255) v = 255;
         out[3ull * q + c] = v;
     }
@@ -410,6 +415,34 @@ __global__ void k_camera_rays(const rtnw_camera cam, int nx, int ny, const int32
     out[q] = o;
 }
 
+// camera::get_ray(s, t) for n (s, t) pairs, PSC/camera.h:41-47: the lens and shutter draws come from the path stream (seed, key_base + q, 0)
+__global__ void k_camera_get_rays(const rtnw_camera cam, const float* __restrict__ st, size_t n, uint64_t seed, uint32_t key_base,
+                                  rtnw_ray* __restrict__ out) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    rng_t g;
+    g.begin((uint32_t)seed, (uint32_t)(seed >> 32), key_base + (uint32_t)q, 0u);
+    ray_t r;
+    camera_get_ray(cam, st[2 * q], st[2 * q + 1], g, r);
+    rtnw_ray o;
+    o.origin[0] = r.o.x; o.origin[1] = r.o.y; o.origin[2] = r.o.z;
+    o.direction[0] = r.d.x; o.direction[1] = r.d.y; o.direction[2] = r.d.z;
+    o.time = r.time;
+    o.key = key_base + (uint32_t)q;
+    out[q] = o;
+}
+
+// rtnw_render_multi: the ranks' float sums added in rank order on device 0; src[r] may be peer memory read over NVLink
+struct rank_planes { const float* src[RTNW_MAX_DEVICES]; int n; };
+__global__ void k_sum_ranks(float* __restrict__ dst, const rank_planes P, size_t count) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        float v = dst[i];
+        for (int r = 1; r < P.n; ++r) v += P.src[r][i];
+        dst[i] = v;
+    }
+}
+
 // ================================================================================================ host side
 namespace {
 
@@ -443,8 +476,10 @@ struct rtnw_ctx {
     size_t accum_floats = 0;
     unsigned long long* fixed = nullptr;  // fixed-point plane of the sample-range split (zero between renders)
     size_t fixed_words = 0;
-    unsigned long long* ctr = nullptr;  // 4 device counters
-    int blocks_per_sm[2] = {0, 0};
+    unsigned long long* ctr = nullptr;       // 8 device counters
+    unsigned long long* ctr_host = nullptr;  // their pinned host copy (filled asynchronously after every render)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // rtnw_render's total_ms
+    int blocks_per_sm[4] = {0, 0, 0, 0};
     // freed scene slabs are kept for the next upload (cudaMalloc/cudaFree synchronise the device and can take
     // milliseconds to hundreds of milliseconds in a process that also hosts another allocator)
     void* spare_slab[2] = {nullptr, nullptr};
@@ -773,23 +808,23 @@ int check_ctx(rtnw_ctx* ctx) {
     return RTNW_OK;
 }
 
-// resident blocks per SM of k_render<COUNT> (cached per context)
-template <bool COUNT>
+// resident blocks per SM of k_render<COUNT, FAST> (cached per context)
+template <bool COUNT, bool FAST>
 int render_occupancy(rtnw_ctx* ctx, int* out) {
-    int& bps = ctx->blocks_per_sm[COUNT ? 1 : 0];
+    int& bps = ctx->blocks_per_sm[(COUNT ? 1 : 0) + (FAST ? 2 : 0)];
     if (bps == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_render<COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT>, RTNW_BLOCK, sizeof(block_smem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_render<COUNT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT, FAST>, RTNW_BLOCK, sizeof(block_smem)));
         if (bps < 1) bps = 1;
     }
     *out = bps;
     return RTNW_OK;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
     int bps = 0;
-    const int rc = render_occupancy<COUNT>(ctx, &bps);
+    const int rc = render_occupancy<COUNT, FAST>(ctx, &bps);
     if (rc != RTNW_OK) return rc;
     int blocks = ctx->sm_count * bps;
     const long long warps_needed = ((long long)a.p.pixel_count * a.chunks + 31) / 32;
@@ -798,7 +833,7 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
 #ifdef RTNW_TUNING  // A/B builds only (scripts/ab_build.sh): the product library reads no environment on the launch path
     if (const char* e = getenv("RTNW_GRID_BLOCKS")) { const int v = atoi(e); if (v > 0) blocks = v; }
 #endif
-    k_render<COUNT><<<blocks, RTNW_BLOCK, sizeof(block_smem), st>>>(a);
+    k_render<COUNT, FAST><<<blocks, RTNW_BLOCK, sizeof(block_smem), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RTNW_OK;
 }
@@ -848,9 +883,16 @@ int validate_params(const rtnw_render_params* p) {
     return RTNW_OK;
 }
 
-// render into a device buffer on stream st; fills stats (kernel_ms from CUDA events on st)
-int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, const rtnw_render_params* p, float* accum_dev,
-                cudaStream_t st, rtnw_stats* stats) {
+// A render in two halves, so that one host thread can keep several devices busy (rtnw_render_multi): render_launch queues
+// everything on stream st and returns; render_finish waits for it and fills stats (kernel_ms from CUDA events on st).
+struct render_ticket {
+    int chunks = 1;
+    rtnw_render_params p;  // with the pixel subset filled in
+    cudaStream_t st = nullptr;
+};
+
+int render_launch(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, const rtnw_render_params* p, float* accum_dev,
+                  cudaStream_t st, render_ticket* ticket) {
     render_args a;
     a.S = scene->view;
     a.cam = *cam;
@@ -879,7 +921,8 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
     }
     CUDA_TRY(cudaMemsetAsync(ctx->ctr, 0, 8 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(ctx->ev0, st));
-    rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true>(ctx, a, st) : launch_render<false>(ctx, a, st);
+    if (p->flags & RTNW_F_FAST_BVH) rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true, true>(ctx, a, st) : launch_render<false, true>(ctx, a, st);
+    else rc = (p->flags & RTNW_F_COUNTERS) ? launch_render<true, false>(ctx, a, st) : launch_render<false, false>(ctx, a, st);
     if (rc != RTNW_OK) return rc;
     if (a.chunks > 1) {
         k_finish_fixed<<<(a.p.pixel_count + 255) / 256, 256, 0, st>>>(a.fixed, a.p.pixel_begin, a.p.pixel_stride, a.p.pixel_count,
@@ -887,9 +930,35 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-    unsigned long long h[8];
-    CUDA_TRY(cudaMemcpyAsync(h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->ctr_host, ctx->ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));  // pinned: truly asynchronous
+    ticket->chunks = a.chunks;
+    ticket->p = a.p;
+    ticket->st = st;
+    return RTNW_OK;
+}
+
+uint64_t paths_of(const rtnw_render_params& p) {  // p: pixel subset filled in
+    if (!(p.flags & RTNW_F_ROTATE_SAMPLES)) return (uint64_t)p.pixel_count * p.sample_count;
+    uint64_t paths = 0;  // per pixel: the samples s = (begin - pixel) mod G + k*G below ns
+    const int g = p.sample_stride;
+    auto floordiv = [](long long x, long long y) { return x >= 0 ? x / y : -((-x + y - 1) / y); };
+    for (int r = 0; r < g; ++r) {  // pixels whose index is r mod G
+        const int b = ((p.sample_begin - r) % g + g) % g;
+        const uint64_t per_pixel = b < p.sample_count ? (uint64_t)(p.sample_count - b + g - 1) / g : 0;
+        uint64_t n_pix = 0;
+        if (p.pixel_stride == 1) {  // integers in [begin, begin+count) congruent to r
+            const long long lo = p.pixel_begin, hi = (long long)p.pixel_begin + p.pixel_count - 1;
+            n_pix = (uint64_t)(floordiv(hi - r, g) - floordiv(lo - 1 - r, g));
+        } else {
+            for (long long k = 0; k < p.pixel_count; ++k) n_pix += ((p.pixel_begin + k * p.pixel_stride) % g) == r;
+        }
+        paths += per_pixel * n_pix;
+    }
+    return paths;
+}
+
+int render_finish(rtnw_ctx* ctx, const render_ticket& t, rtnw_stats* stats) {
+    CUDA_TRY(cudaStreamSynchronize(t.st));
 #ifdef RTNW_ROUND_STATS
     {
         unsigned long long rs[32];
@@ -904,37 +973,28 @@ int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
         cudaMemcpyToSymbol(g_round_stats, z, sizeof z);
     }
 #endif
+    const unsigned long long* h = ctx->ctr_host;
     if (h[4]) return fail(RTNW_ERR_UNSUPPORTED, "BVH task stack overflow: the tree is deeper than RTNW_QN/RTNW_BLOCK - 1 levels");
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
-        if (p->flags & RTNW_F_ROTATE_SAMPLES) {  // per pixel: the samples s = (begin - p) mod G + k*G below ns
-            uint64_t paths = 0;
-            const int g = p->sample_stride;
-            auto floordiv = [](long long x, long long y) { return x >= 0 ? x / y : -((-x + y - 1) / y); };
-            for (int r = 0; r < g; ++r) {  // pixels whose index is r mod G
-                const int b = ((p->sample_begin - r) % g + g) % g;
-                const uint64_t per_pixel = b < p->sample_count ? (uint64_t)(p->sample_count - b + g - 1) / g : 0;
-                uint64_t n_pix = 0;
-                if (a.p.pixel_stride == 1) {  // integers in [begin, begin+count) congruent to r
-                    const long long lo = a.p.pixel_begin, hi = (long long)a.p.pixel_begin + a.p.pixel_count - 1;
-                    n_pix = (uint64_t)(floordiv(hi - r, g) - floordiv(lo - 1 - r, g));
-                } else {
-                    for (long long k = 0; k < a.p.pixel_count; ++k) n_pix += ((a.p.pixel_begin + k * a.p.pixel_stride) % g) == r;
-                }
-                paths += per_pixel * n_pix;
-            }
-            stats->paths = paths;
-        } else {
-            stats->paths = (uint64_t)a.p.pixel_count * p->sample_count;
-        }
+        stats->paths = paths_of(t.p);
         stats->rays = h[1];
         stats->box_tests = h[2];
         stats->prim_tests = h[3];
         CUDA_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev0, ctx->ev1));
-        stats->kernel_launches = a.chunks > 1 ? 2 : 1;
-        stats->sample_ranges = a.chunks;
+        stats->kernel_launches = t.chunks > 1 ? 2 : 1;
+        stats->sample_ranges = t.chunks;
     }
     return RTNW_OK;
+}
+
+// render into a device buffer on stream st, synchronously
+int render_core(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, const rtnw_render_params* p, float* accum_dev,
+                cudaStream_t st, rtnw_stats* stats) {
+    render_ticket t;
+    const int rc = render_launch(ctx, scene, cam, p, accum_dev, st, &t);
+    if (rc != RTNW_OK) return rc;
+    return render_finish(ctx, t, stats);
 }
 
 }  // namespace
@@ -979,7 +1039,10 @@ int rtnw_ctx_create(int device, rtnw_ctx** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_t1);
     if (e == cudaSuccess) e = cudaMalloc(&c->ctr, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->ctr_host, 8 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         rtnw_ctx_destroy(c);
         return fail(RTNW_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
@@ -995,6 +1058,9 @@ int rtnw_ctx_destroy(rtnw_ctx* c) {
     if (c->fixed) cudaFree(c->fixed);
     for (int q = 0; q < 2; ++q) if (c->spare_slab[q]) cudaFree(c->spare_slab[q]);
     if (c->ctr) cudaFree(c->ctr);
+    if (c->ctr_host) cudaFreeHost(c->ctr_host);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1184,21 +1250,14 @@ int rtnw_render(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_camera* cam, 
         }
         ctx->accum_floats = floats;
     }
-    cudaEvent_t t0, t1;
-    CUDA_TRY(cudaEventCreate(&t0));
-    CUDA_TRY(cudaEventCreate(&t1));
-    CUDA_TRY(cudaEventRecord(t0, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_t0, ctx->stream));
     rc = render_core(ctx, scene, cam, params, ctx->accum, ctx->stream, stats);
-    if (rc == RTNW_OK) {
-        cudaError_t e = cudaMemcpyAsync(accum_rgb, ctx->accum, floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(t1, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(RTNW_ERR_CUDA, std::string("result copy: ") + cudaGetErrorString(e));
-        else if (stats) cudaEventElapsedTime(&stats->total_ms, t0, t1);
-    }
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
-    return rc;
+    if (rc != RTNW_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(accum_rgb, ctx->accum, floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) CUDA_TRY(cudaEventElapsedTime(&stats->total_ms, ctx->ev_t0, ctx->ev_t1));
+    return RTNW_OK;
 }
 
 int rtnw_plan_sample_ranges(const rtnw_render_params* params, int32_t* cum, int32_t cap) {
@@ -1237,10 +1296,14 @@ int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, siz
     CUDA_TRY(d_rays.alloc(n * sizeof(rtnw_ray)));
     CUDA_TRY(d_out.alloc(n * sizeof(rtnw_hit)));
     CUDA_TRY(cudaMemcpyAsync(d_rays.p, rays, n * sizeof(rtnw_ray), cudaMemcpyHostToDevice, ctx->stream));
-    (void)flags;  // RTNW_F_CULL_NARROW is accepted for ABI compatibility; the cooperative traversal is always reference-exact
-    CUDA_TRY(cudaFuncSetAttribute(k_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
-    k_trace<<<(unsigned)((n + RTNW_BLOCK - 1) / RTNW_BLOCK), RTNW_BLOCK, sizeof(block_smem), ctx->stream>>>(
-        scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
+    const unsigned grid = (unsigned)((n + RTNW_BLOCK - 1) / RTNW_BLOCK);
+    if (flags & RTNW_F_FAST_BVH) {
+        CUDA_TRY(cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
+        k_trace<true><<<grid, RTNW_BLOCK, sizeof(block_smem), ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
+        k_trace<false><<<grid, RTNW_BLOCK, sizeof(block_smem), ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n * sizeof(rtnw_hit), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1328,6 +1391,190 @@ int rtnw_camera_rays(rtnw_ctx* ctx, const rtnw_camera* cam, int32_t nx, int32_t 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(rays_out, d_out.p, n * sizeof(rtnw_ray), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
+}
+
+int rtnw_camera_get_rays(rtnw_ctx* ctx, const rtnw_camera* cam, const float* st, size_t n, uint64_t seed, uint32_t key_base,
+                         rtnw_ray* rays_out) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!cam || (n && (!st || !rays_out))) return fail(RTNW_ERR_INVALID, "bad argument");
+    if (n == 0) return RTNW_OK;
+    dev_buf d_st, d_out;
+    CUDA_TRY(d_st.alloc(n * 2 * sizeof(float)));
+    CUDA_TRY(d_out.alloc(n * sizeof(rtnw_ray)));
+    CUDA_TRY(cudaMemcpyAsync(d_st.p, st, n * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_camera_get_rays<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(*cam, d_st.as<float>(), n, seed, key_base, d_out.as<rtnw_ray>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rays_out, d_out.p, n * sizeof(rtnw_ray), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTNW_OK;
+}
+
+// ---- N GPUs of one box behind one handle: one host thread, one context + stream per device --------------
+struct rtnw_multi {
+    int n = 0;
+    rtnw_ctx* ctx[RTNW_MAX_DEVICES] = {};
+    float* accum[RTNW_MAX_DEVICES] = {};   // per device: nx*ny*3 sums of its share of the samples
+    size_t accum_floats = 0;
+    cudaEvent_t done[RTNW_MAX_DEVICES] = {};
+    bool peer[RTNW_MAX_DEVICES] = {};      // device 0 reads this rank's buffer directly (same device, or P2P over NVLink)
+    float* stage = nullptr;                // device 0: copies of the buffers it cannot read directly
+    size_t stage_floats = 0;
+};
+struct rtnw_multi_scene {
+    int n = 0;
+    rtnw_scene* scene[RTNW_MAX_DEVICES] = {};
+};
+
+int rtnw_ctx_destroy_multi(rtnw_multi* m) {
+    if (!m) return RTNW_OK;
+    for (int d = 0; d < m->n; ++d) {
+        if (!m->ctx[d]) continue;
+        cudaSetDevice(m->ctx[d]->device);
+        if (m->accum[d]) cudaFree(m->accum[d]);
+        if (m->done[d]) cudaEventDestroy(m->done[d]);
+        if (d == 0 && m->stage) cudaFree(m->stage);
+        rtnw_ctx_destroy(m->ctx[d]);
+    }
+    delete m;
+    return RTNW_OK;
+}
+
+int rtnw_ctx_create_multi(const int* device_ids, int n, rtnw_multi** out) {
+    if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (!device_ids || n < 1 || n > RTNW_MAX_DEVICES) return fail(RTNW_ERR_INVALID, "bad device list");
+    rtnw_multi* m = new rtnw_multi();
+    m->n = n;
+    for (int d = 0; d < n; ++d) {
+        int rc = rtnw_ctx_create(device_ids[d], &m->ctx[d]);
+        if (rc == RTNW_OK && cudaEventCreateWithFlags(&m->done[d], cudaEventDisableTiming) != cudaSuccess) rc = fail(RTNW_ERR_CUDA, "event creation failed");
+        if (rc != RTNW_OK) { const std::string msg = g_err; rtnw_ctx_destroy_multi(m); return fail(rc, msg); }
+    }
+    // device 0 adds the other ranks' buffers: directly over NVLink where peer access exists, else through a staging copy
+    const int dev0 = m->ctx[0]->device;
+    for (int d = 0; d < n; ++d) {
+        const int dev = m->ctx[d]->device;
+        if (dev == dev0) { m->peer[d] = true; continue; }
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, dev0, dev);
+        if (can) {
+            cudaSetDevice(dev0);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+            cudaGetLastError();
+        }
+        m->peer[d] = can != 0;
+    }
+    *out = m;
+    return RTNW_OK;
+}
+
+int rtnw_multi_device_count(const rtnw_multi* m) { return m ? m->n : 0; }
+
+int rtnw_scene_free_multi(rtnw_multi* m, rtnw_multi_scene* ms) {
+    if (!ms) return RTNW_OK;
+    for (int d = 0; d < ms->n; ++d)
+        if (ms->scene[d]) rtnw_scene_free(m && d < m->n ? m->ctx[d] : nullptr, ms->scene[d]);
+    delete ms;
+    return RTNW_OK;
+}
+
+int rtnw_scene_upload_multi(rtnw_multi* m, const rtnw_scene_desc* desc, rtnw_multi_scene** out) {
+    if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (!m) return fail(RTNW_ERR_INVALID, "null context");
+    rtnw_multi_scene* ms = new rtnw_multi_scene();
+    ms->n = m->n;
+    for (int d = 0; d < m->n; ++d) {
+        const int rc = rtnw_scene_upload(m->ctx[d], desc, &ms->scene[d]);
+        if (rc != RTNW_OK) { const std::string msg = g_err; rtnw_scene_free_multi(m, ms); return fail(rc, msg); }
+    }
+    *out = ms;
+    return RTNW_OK;
+}
+
+int rtnw_render_multi(rtnw_multi* m, const rtnw_multi_scene* ms, const rtnw_camera* cam, const rtnw_render_params* params,
+                      float* accum_rgb, rtnw_stats* stats) {
+    if (!m || !ms || ms->n != m->n || !cam || !accum_rgb) return fail(RTNW_ERR_INVALID, "null argument");
+    int rc = validate_params(params);
+    if (rc != RTNW_OK) return rc;
+    if (params->pixel_count != 0 || params->sample_begin != 0 || params->sample_stride != 1 ||
+        (params->flags & (RTNW_F_ACCUMULATE | RTNW_F_ROTATE_SAMPLES)))
+        return fail(RTNW_ERR_INVALID, "rtnw_render_multi renders whole frames: sample_begin 0, sample_stride 1, no pixel subset, no ACCUMULATE / ROTATE flags");
+    const int n = m->n;
+    const size_t floats = (size_t)params->nx * params->ny * 3;
+    int need_stage = 0;
+    for (int d = 1; d < n; ++d) need_stage += m->peer[d] ? 0 : 1;
+    if (m->accum_floats < floats || (need_stage && m->stage_floats < floats * need_stage)) {
+        for (int d = 0; d < n; ++d) {
+            CUDA_TRY(cudaSetDevice(m->ctx[d]->device));
+            if (m->accum[d]) cudaFree(m->accum[d]);
+            m->accum[d] = nullptr;
+            if (cudaMalloc(&m->accum[d], floats * sizeof(float)) != cudaSuccess) { cudaGetLastError(); m->accum_floats = 0; return fail(RTNW_ERR_NOMEM, "cannot allocate the per-device accumulation buffers"); }
+        }
+        m->accum_floats = floats;
+        if (need_stage) {
+            CUDA_TRY(cudaSetDevice(m->ctx[0]->device));
+            if (m->stage) cudaFree(m->stage);
+            m->stage = nullptr;
+            if (cudaMalloc(&m->stage, floats * need_stage * sizeof(float)) != cudaSuccess) { cudaGetLastError(); m->stage_floats = 0; return fail(RTNW_ERR_NOMEM, "cannot allocate the staging planes"); }
+            m->stage_floats = floats * need_stage;
+        }
+    }
+    // every device renders its share of every pixel's samples (ownership rotates with the pixel index: even for any ns)
+    render_ticket ticket[RTNW_MAX_DEVICES];
+    CUDA_TRY(cudaSetDevice(m->ctx[0]->device));
+    CUDA_TRY(cudaEventRecord(m->ctx[0]->ev_t0, m->ctx[0]->stream));
+    for (int d = 0; d < n; ++d) {
+        rtnw_ctx* c = m->ctx[d];
+        CUDA_TRY(cudaSetDevice(c->device));
+        rtnw_render_params p = *params;
+        if (n > 1) { p.flags |= RTNW_F_ROTATE_SAMPLES; p.sample_begin = d; p.sample_stride = n; }
+        rc = render_launch(c, ms->scene[d], cam, &p, m->accum[d], c->stream, &ticket[d]);
+        if (rc != RTNW_OK) return rc;
+        CUDA_TRY(cudaEventRecord(m->done[d], c->stream));
+    }
+    // one sum on device 0, in rank order (deterministic), then the frame goes to the host
+    rtnw_ctx* c0 = m->ctx[0];
+    CUDA_TRY(cudaSetDevice(c0->device));
+    if (n > 1) {
+        rank_planes P;
+        P.n = n;
+        int staged = 0;
+        for (int d = 1; d < n; ++d) {
+            CUDA_TRY(cudaStreamWaitEvent(c0->stream, m->done[d], 0));
+            if (m->peer[d]) P.src[d] = m->accum[d];
+            else {
+                float* dst = m->stage + floats * (size_t)staged++;
+                CUDA_TRY(cudaMemcpyPeerAsync(dst, c0->device, m->accum[d], m->ctx[d]->device, floats * sizeof(float), c0->stream));
+                P.src[d] = dst;
+            }
+        }
+        P.src[0] = m->accum[0];
+        k_sum_ranks<<<c0->sm_count * 8, 256, 0, c0->stream>>>(m->accum[0], P, floats);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(accum_rgb, m->accum[0], floats * sizeof(float), cudaMemcpyDeviceToHost, c0->stream));
+    CUDA_TRY(cudaEventRecord(c0->ev_t1, c0->stream));
+    rtnw_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (int d = 0; d < n; ++d) {
+        CUDA_TRY(cudaSetDevice(m->ctx[d]->device));
+        rtnw_stats st;
+        rc = render_finish(m->ctx[d], ticket[d], &st);
+        if (rc != RTNW_OK) return rc;
+        total.paths += st.paths; total.rays += st.rays; total.box_tests += st.box_tests; total.prim_tests += st.prim_tests;
+        total.kernel_ms = std::max(total.kernel_ms, st.kernel_ms);
+        total.kernel_launches += st.kernel_launches;
+        total.sample_ranges = std::max(total.sample_ranges, st.sample_ranges);
+    }
+    CUDA_TRY(cudaSetDevice(c0->device));
+    CUDA_TRY(cudaStreamSynchronize(c0->stream));
+    CUDA_TRY(cudaEventElapsedTime(&total.total_ms, c0->ev_t0, c0->ev_t1));
+    if (n > 1) total.kernel_launches += 1;
+    if (stats) *stats = total;
     return RTNW_OK;
 }
 

@@ -501,7 +501,17 @@ struct coop_smem {
     unsigned lh[3];       // gate queue head (consumed), same rotation; counts up for the whole kernel, index = value % QL
     unsigned lt;          // gate queue tail (produced); never reset
     int overflow;         // a push did not fit (cannot happen for validated scenes); reported to the host
+    // warp-asynchronous traversal (async_bvh_item): q is re-cut into per-warp private stacks + two shared rings
+    unsigned ring_head[2], ring_tail[2];  // [0] node ring, [1] gate ring; monotonic counters, index = value % ARING
+    int idle[2];          // warps that found no work (per phase parity)
 };
+#ifndef RTNW_ASYNC
+#define RTNW_ASYNC 0
+#endif
+#define RTNW_ANW 256     // private node-task stack of a warp
+#define RTNW_AGW 256     // private gate-task stack of a warp
+#define RTNW_ARING 1024  // shared ring (one for node tasks, one for gate tasks), a power of two
+#define RTNW_EMPTY 0xffffffffu
 // task = owner slot (9 bits) | wide node index or gate index (23 bits)
 #define RTNW_IDX_BITS 23
 #define RTNW_TASK(slot, idx) (((uint32_t)(slot) << RTNW_IDX_BITS) | (uint32_t)(idx))
@@ -514,6 +524,11 @@ __device__ __forceinline__ void coop_init(coop_smem<GROUP>& sm) {
     const int tid = threadIdx.x % GROUP;
     if (tid < 3) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
     if (tid == 3) { sm.lt = 0u; sm.overflow = 0; }
+#if RTNW_ASYNC
+    static_assert((GROUP / 32) * (RTNW_ANW + RTNW_AGW) + 2 * RTNW_ARING <= coop_smem<GROUP>::QN + coop_smem<GROUP>::QL, "async queues do not fit q[]");
+    if (tid < 2) { sm.ring_head[tid] = 0u; sm.ring_tail[tid] = 0u; sm.idle[tid] = 0; }
+    for (int i = tid; i < 2 * RTNW_ARING; i += GROUP) sm.q[(GROUP / 32) * (RTNW_ANW + RTNW_AGW) + i] = RTNW_EMPTY;
+#endif
 }
 
 // Closest hit of the block's rays against the BVH item whose gate tree has root `root`.  Owners have already written
@@ -523,7 +538,7 @@ __device__ __forceinline__ void coop_init(coop_smem<GROUP>& sm) {
 // lane from the top of the stack; the remaining warps take one queued gate per lane (leaf->hit for its leaves), so
 // thin node rounds are filled with leaf work instead of idling at the barrier; when the stack is empty all warps
 // drain the gate queue.
-template <int GROUP, bool COUNT>
+template <int GROUP, bool COUNT, bool FAST>
 __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GROUP>& sm, int root, int tree_depth, bool active,
                                               float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt, int& r3) {
     constexpr unsigned FULL = 0xffffffffu;
@@ -587,11 +602,14 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
             const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
             const int ref[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
+            // RTNW_F_FAST_BVH: boxes are tested against the ray's closest hit SO FAR (any value read is a valid upper bound:
+            // the key only ever decreases) instead of the un-narrowed range the reference hands down
+            const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[slot], ro.w)) : ro.w;
             bool pass[4];
-            pass[0] = live & (ref[0] != RTNW_REF_NONE) & hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, ro.w);
-            pass[1] = live & (ref[1] != RTNW_REF_NONE) & hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, ro.w);
-            pass[2] = live & (ref[2] != RTNW_REF_NONE) & hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, ro.w);
-            pass[3] = live & (ref[3] != RTNW_REF_NONE) & hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, ro.w);
+            pass[0] = live & (ref[0] != RTNW_REF_NONE) & hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, t_hi);
+            pass[1] = live & (ref[1] != RTNW_REF_NONE) & hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, t_hi);
+            pass[2] = live & (ref[2] != RTNW_REF_NONE) & hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, t_hi);
+            pass[3] = live & (ref[3] != RTNW_REF_NONE) & hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, t_hi);
             if (COUNT && live) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
 #if RTNW_PREFETCH
             {   // the children that passed are popped a round (>= 1000 cycles) from now: pull their lines into L1 off the critical path
@@ -655,7 +673,8 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
                 const uint4 mq = sm.mkey[slot];
                 ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
                 medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-                k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, ro.w, mk, cnt);
+                const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[slot], ro.w)) : ro.w;
+                k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, t_hi, mk, cnt);
             }
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
         }
@@ -670,9 +689,211 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
 #endif
 }
 
+// ---- warp-asynchronous BVH item ------------------------------------------------------------------------------
+// Same tasks, same results as coop_bvh_item, without rounds: inside the item no block barrier is executed.  Every warp
+// owns a private LIFO stack of node tasks and one of gate tasks (height in registers, pushes by ballot prefix, no atomics)
+// and works on batches of 32 node tasks or 16 gates (two lanes each) on its own.  Load is balanced through two shared
+// rings: a warp with more than two batches of work donates a batch, a warp whose batch is not full tops it up from the
+// ring, a warp without work steals.  A task names its ray's slot, so any warp can run it (candidates merge with atomicMin
+// on the slot's key).  The item ends when every warp is idle: a warp counts itself idle only after a failed steal with
+// empty private stacks and leaves that state BEFORE it takes anything from a ring, so "all idle" implies that no task is
+// left anywhere.  Memory stays bounded by the same rule as before (a batch shrinks as the private stack fills: plain
+// depth-first descent in the worst case), and a donation happens only when the ring has room.
+__device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+__device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// take up to `want` tasks from ring `which` into dst[0..got); warp-uniform result
+template <int GROUP>
+__device__ __forceinline__ int ring_steal(coop_smem<GROUP>& sm, uint32_t* ring, int which, int want, uint32_t* dst, unsigned lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    int got = 0;
+    unsigned h = 0;
+    if (lane == 0) {
+        for (;;) {
+            h = ld_vol(&sm.ring_head[which]);
+            const int avail = (int)(ld_vol(&sm.ring_tail[which]) - h);
+            if (avail <= 0) { got = 0; break; }
+            got = min(avail, want);
+            if (atomicCAS(&sm.ring_head[which], h, h + (unsigned)got) == h) break;
+        }
+    }
+    got = __shfl_sync(FULL, got, 0);
+    h = __shfl_sync(FULL, h, 0);
+    if ((int)lane < got) {
+        volatile uint32_t* slot = ring + ((h + lane) & (RTNW_ARING - 1));
+        uint32_t v;
+        while ((v = *slot) == RTNW_EMPTY) {}  // reserved by a donor that is about to write it
+        *slot = RTNW_EMPTY;
+        dst[lane] = v;
+    }
+    __syncwarp();
+    return got;
+}
+// give src[0..k) (k <= 32) to ring `which` if it has room; warp-uniform result
+template <int GROUP>
+__device__ __forceinline__ bool ring_donate(coop_smem<GROUP>& sm, uint32_t* ring, int which, int k, const uint32_t* src, unsigned lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    int ok = 0;
+    unsigned t = 0;
+    if (lane == 0) {
+        const int used = (int)(ld_vol(&sm.ring_tail[which]) - ld_vol(&sm.ring_head[which]));
+        if (used + k <= RTNW_ARING - 32 * (GROUP / 32)) {  // all warps may pass this check at once: 32 entries of slack each
+            t = atomicAdd(&sm.ring_tail[which], (unsigned)k);
+            ok = 1;
+        }
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    if (!ok) return false;
+    t = __shfl_sync(FULL, t, 0);
+    __threadfence_block();  // whatever this warp wrote for these tasks' rays is visible before the tasks are
+    if ((int)lane < k) {
+        volatile uint32_t* slot = ring + ((t + lane) & (RTNW_ARING - 1));
+        while (*slot != RTNW_EMPTY) {}  // the previous lap's taker has not cleared it yet
+        *slot = src[lane];
+    }
+    __syncwarp();
+    return true;
+}
+
+template <int GROUP, bool COUNT>
+__device__ __forceinline__ void async_bvh_item(const scene_view& S, coop_smem<GROUP>& sm, int root, int tree_depth, bool active,
+                                               float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt, int& phase) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NWARP = GROUP / 32, NW = RTNW_ANW, GW = RTNW_AGW;
+    const int tid = threadIdx.x % GROUP;
+    const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+    const int warp = tid >> 5;
+    uint32_t* const myN = sm.q + warp * (NW + GW);
+    uint32_t* const myG = myN + NW;
+    uint32_t* const ringN = sm.q + NWARP * (NW + GW);
+    uint32_t* const ringG = ringN + RTNW_ARING;
+    const int ph = phase & 1;
+    if (tid == 0) sm.idle[ph ^ 1] = 0;  // the other parity: last read before the barrier that ended the previous item
+    int nN, nG = 0;
+    {   // one task per ray: the root of the gate tree
+        const unsigned b = __ballot_sync(FULL, active);
+        if (active) myN[__popc(b & lt_mask)] = RTNW_TASK(tid, root);
+        nN = __popc(b);
+    }
+    __syncwarp();
+    bool idle = false;
+#pragma unroll 1
+    for (;;) {
+        if (nN == 0 && nG == 0) {
+            // ---- nothing of my own: steal, or wait for the others to finish
+            if (idle) {  // decided by lane 0 and broadcast: every lane must take the same branch
+                int st = 0;  // 0 wait, 1 rings hold something, 2 every warp is idle
+                if (lane == 0) {
+                    const bool some = (int)(ld_vol(&sm.ring_tail[0]) - ld_vol(&sm.ring_head[0])) > 0 ||
+                                      (int)(ld_vol(&sm.ring_tail[1]) - ld_vol(&sm.ring_head[1])) > 0;
+                    if (some) { atomicSub(&sm.idle[ph], 1); st = 1; }  // leave the idle state BEFORE taking a task
+                    else if (ld_vol(&sm.idle[ph]) == NWARP) st = 2;
+                    else __nanosleep(64);  // leave the issue slots to the warps that have work
+                }
+                st = __shfl_sync(FULL, st, 0);
+                if (st == 2) break;
+                if (st == 0) continue;
+                __threadfence_block();
+                idle = false;
+            }
+            nN = ring_steal<GROUP>(sm, ringN, 0, 32, myN, lane);
+            if (nN == 0) nG = ring_steal<GROUP>(sm, ringG, 1, 16, myG, lane);
+            if (nN == 0 && nG == 0) {
+                idle = true;
+                if (lane == 0) atomicAdd(&sm.idle[ph], 1);
+                __syncwarp();
+                continue;
+            }
+            __threadfence_block();  // acquire: the donor's writes (ray state of foreign slots)
+            RTNW_STAT(4, 1);
+        }
+        if (nN > 0 && nG < 64) {
+            // ---- node batch: one wide node per lane
+            const int room = (NW - nN - 3 * tree_depth) / 3;
+            int take = min(min(nN, 32), min(max(room, 1), (GW - nG) >> 2));
+            if (take == nN && take < 32 && room >= 32) {  // top the batch up (ring_steal returns 0 at once when the ring is empty)
+                const int got = ring_steal<GROUP>(sm, ringN, 0, 32 - take, myN + nN, lane);
+                if (got) __threadfence_block();
+                nN += got; take += got;
+            }
+            const bool live = (int)lane < take;
+            const uint32_t task = live ? myN[nN - take + (int)lane] : 0u;
+            nN -= take;
+            RTNW_STAT(0, 1); RTNW_STAT(1, take);
+            const int slot = RTNW_TASK_SLOT(task);
+            const float4* N = S.wnodes + 8 * (size_t)RTNW_TASK_IDX(task);
+            const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
+            const float4 rf = __ldg(N + 6);
+            const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
+            const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
+            const int ref[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
+            bool pass[4];
+            pass[0] = live & (ref[0] != RTNW_REF_NONE) & hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, ro.w);
+            pass[1] = live & (ref[1] != RTNW_REF_NONE) & hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, ro.w);
+            pass[2] = live & (ref[2] != RTNW_REF_NONE) & hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, ro.w);
+            pass[3] = live & (ref[3] != RTNW_REF_NONE) & hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, ro.w);
+            if (COUNT && live) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
+            __syncwarp();  // every lane has read its task before the stack is written
+            int at_n = nN, at_l = nG;
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool isn = ref[j] >= 0;
+                const unsigned bn = __ballot_sync(FULL, pass[j] & isn), bl = __ballot_sync(FULL, pass[j] & !isn);
+                const int pn = at_n + __popc(bn & lt_mask), pl = at_l + __popc(bl & lt_mask);
+                const bool fits = isn ? pn < NW : pl < GW;
+                if (pass[j] & fits) (isn ? myN : myG)[isn ? pn : pl] = RTNW_TASK(slot, isn ? ref[j] : ~ref[j]);
+                ok &= !pass[j] | fits;
+                at_n += __popc(bn); at_l += __popc(bl);
+            }
+            if (!ok) sm.overflow = 1;
+            nN = min(at_n, NW); nG = min(at_l, GW);
+            __syncwarp();
+        } else {
+            // ---- gate batch: leaf->hit(r, tmin, tmax0) for the one or two leaves of 16 gates, one lane per leaf
+            int take = min(nG, 16);
+            if (take == nG && take < 16) {
+                const int got = ring_steal<GROUP>(sm, ringG, 1, 16 - take, myG + nG, lane);
+                if (got) __threadfence_block();
+                nG += got; take += got;
+            }
+            const bool live = (int)(lane >> 1) < take;
+            const uint32_t task = live ? myG[nG - take + (int)(lane >> 1)] : 0u;
+            nG -= take;
+            RTNW_STAT(2, 1); RTNW_STAT(3, take);
+            if (live) {
+                const int slot = RTNW_TASK_SLOT(task);
+                const int2 g = __ldg(&S.gates[RTNW_TASK_IDX(task)]);
+                const int leaf = (lane & 1) ? g.y : g.x;
+                if (leaf >= 0) {
+                    const float4 A0 = __ldg(&S.recs[leaf].a), B0 = __ldg(&S.recs[leaf].b);
+                    const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
+                    const uint4 mq = sm.mkey[slot];
+                    ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+                    medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
+                    const hkey_t k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, ro.w, mk, cnt);
+                    if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- share: more than two batches of one kind -> one batch goes to the ring (if it has room)
+#ifndef RTNW_ASYNC_NODONATE
+        if (nN >= 64) {
+            if (ring_donate<GROUP>(sm, ringN, 0, 32, myN + nN - 32, lane)) { nN -= 32; RTNW_STAT(5, 1); }
+        }
+        if (nG >= 48) {
+            if (ring_donate<GROUP>(sm, ringG, 1, 16, myG + nG - 16, lane)) { nG -= 16; RTNW_STAT(6, 1); }
+        }
+#endif
+    }
+    phase++;
+    group_sync<GROUP>();  // every candidate has been merged into sm.key before any owner reads its result
+}
+
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
 // thread without a ray passes active = false and still works on the other threads' BVH tasks.
-template <int GROUP, bool COUNT>
+template <int GROUP, bool COUNT, bool FAST>
 __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_smem<GROUP>& sm, const ray_t& wr, bool active,
                                                    float t_min, float t_max, const medium_key& mk, trav_counters& cnt, int& r3) {
     const int tid = threadIdx.x % GROUP;
@@ -693,7 +914,12 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
             sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
             sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
             sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-            coop_bvh_item<GROUP, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
+#if RTNW_ASYNC
+            __syncwarp();
+            async_bvh_item<GROUP, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
+#else
+            coop_bvh_item<GROUP, COUNT, FAST>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
+#endif
         } else if (active) {
             float lim = best_t;
 #pragma unroll 1
@@ -942,9 +1168,8 @@ __device__ __forceinline__ bool material_scatter(const scene_view& S, int mat, c
 // ------------------------------------------------------------------------------------------------ camera
 // PSC/main.cpp:305-306 + PSC/camera.h:41-56.  Draw order of the path's sequential stream: jitter u, jitter v,
 // disk (first draw -> y, second -> x, g++ right-to-left), time.
-__device__ __forceinline__ void camera_ray(const rtnw_camera& c, int nx, int ny, int i, int j, rng_t& g, ray_t& r) {
-    const float s = ((float)i + g.draw()) / (float)nx;  // float(i + drand48()): the double sum is exact, one rounding
-    const float t = ((float)j + g.draw()) / (float)ny;
+// camera::get_ray(s, t), PSC/camera.h:41-56
+__device__ __forceinline__ void camera_get_ray(const rtnw_camera& c, float s, float t, rng_t& g, ray_t& r) {
     float px, py;
     do {
         const float dy = g.draw(), dx = g.draw();
@@ -961,6 +1186,11 @@ __device__ __forceinline__ void camera_ray(const rtnw_camera& c, int nx, int ny,
     r.o = org + offset;
     r.d = llc + s * hor + t * ver - org - offset;
     r.time = time;
+}
+__device__ __forceinline__ void camera_ray(const rtnw_camera& c, int nx, int ny, int i, int j, rng_t& g, ray_t& r) {
+    const float s = ((float)i + g.draw()) / (float)nx;  // float(i + drand48()): the double sum is exact, one rounding
+    const float t = ((float)j + g.draw()) / (float)ny;
+    camera_get_ray(c, s, t, g, r);
 }
 
 // TNW/Chapter01_Motion Blur.cpp:29-31

@@ -32,6 +32,14 @@ const char* rtnw_host_last_error(void) { return g_err.c_str(); }
 int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
     if (!name_c || !out) return fail(RTNW_ERR_INVALID, "null argument");
     std::string name(name_c);
+    // ":chNN" suffix: the camera / integrator settings of that chapter snapshot's main() instead of the live main()'s
+    // (SURVEY.md §3.4): ch01 and ch03 use t_min 0.0 (TNW/Chapter01_Motion Blur.cpp:16), ch07 and ch08 t_min 0.01, aperture 0.1,
+    // 200x200x100 and neither de_nan nor clamp (TNW/Chapter07_Instance.cpp:25,165-178, TNW/Chapter08_Volume.cpp:26,188-253)
+    std::string snapshot;
+    const size_t colon = name.find(':');
+    if (colon != std::string::npos) { snapshot = name.substr(colon + 1); name.erase(colon); }
+    if (!snapshot.empty() && snapshot != "ch01" && snapshot != "ch03" && snapshot != "ch07" && snapshot != "ch08")
+        return fail(RTNW_ERR_INVALID, "unknown chapter snapshot view: " + snapshot);
     bool wrap = false;
     const size_t plus = name.find("+bvh");
     if (plus != std::string::npos) {
@@ -65,8 +73,14 @@ int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
     else if (name == "random_scene") { world = random_scene(); v = view_ch01(); v.emit = true; }
     else if (name == "test") { world = test_scene(); v = view_two_perlin(); v.sky = false; v.emit = true; }
     else if (name == "stress_shells") { world = stress_shells(); v = view_ch01(); v.aperture = 0.0f; }
+    else if (name == "twin_bvh") { world = twin_bvh(); v = view_ch01(); v.aperture = 0.0f; }
     else return fail(RTNW_ERR_INVALID, "unknown scene name: " + name);
     if (wrap) world = wrap_in_bvh(world, 0, 1);
+    if (snapshot == "ch01" || snapshot == "ch03") {
+        v.t_min = 0.0f; v.aperture = 0.1f; v.nx = 200; v.ny = 100; v.ns = 100; v.sky = true; v.emit = false; v.de_nan = false;
+    } else if (snapshot == "ch07" || snapshot == "ch08") {
+        v.t_min = 0.01f; v.aperture = 0.1f; v.nx = 200; v.ny = 200; v.ns = 100; v.lookfrom = vec3(278, 278, -800); v.de_nan = false;
+    }
 
     rtnw_host_scene* s = new rtnw_host_scene();
     const int rc = rtnw::flatten(world, s->flat);

@@ -1,0 +1,3 @@
+// drop-in for the reference header of the same name (PSC/hitable.h): every class lives in rtnw/scene.hpp
+#pragma once
+#include "rtnw/scene.hpp"

@@ -1,0 +1,3 @@
+// drop-in for the reference header of the same name (PSC/surface_texture.h): every class lives in rtnw/scene.hpp
+#pragma once
+#include "rtnw/scene.hpp"

@@ -122,6 +122,15 @@ vec3 bridge_value(const texture* t, float u, float v, const vec3& p) {
     return vec3(rgb[0], rgb[1], rgb[2]);
 }
 
+ray bridge_get_ray(const camera* cam, float s, float t) {
+    rtnw_camera c;
+    to_c_camera(*cam, c);
+    const float st[2] = {s, t};
+    rtnw_ray out;
+    if (rtnw_camera_get_rays(g_ctx, &c, st, 1, g_seed, g_calls++, &out) != RTNW_OK) die("rtnw_camera_get_rays");
+    return ray(vec3(out.origin[0], out.origin[1], out.origin[2]), vec3(out.direction[0], out.direction[1], out.direction[2]), out.time);
+}
+
 }  // namespace
 
 // Route the reference API's virtuals to GPU `device`.  Returns an rtnw_status.
@@ -133,6 +142,7 @@ int install_cuda_bridge(int device, unsigned long long seed) {
     b.scatter = bridge_scatter;
     b.emitted = bridge_emitted;
     b.value = bridge_value;
+    b.get_ray = bridge_get_ray;
     set_device_bridge(b);
     return RTNW_OK;
 }

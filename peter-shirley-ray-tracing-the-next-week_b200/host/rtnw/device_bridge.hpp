@@ -1,5 +1,6 @@
 // The reference API has four virtuals that do arithmetic on the hot path (hitable::hit, material::scatter,
-// material::emitted, texture::value; PSC/hitable.h:34, PSC/material.h:54-57, PSC/texture.h:13).  In this
+// material::emitted, texture::value; PSC/hitable.h:34, PSC/material.h:54-57, PSC/texture.h:13) and camera::get_ray
+// (PSC/camera.h:41-47).  In this
 // framework they have no CPU implementation: a bridge forwards single calls to the GPU library
 // (rtnw_trace / rtnw_scatter / rtnw_eval_texture).  Without an installed bridge the calls abort loudly.
 #ifndef RTNW_DEVICE_BRIDGE_HPP_
@@ -13,6 +14,7 @@ struct device_bridge {
     bool (*scatter)(const material*, const ray&, const hit_record&, vec3&, ray&) = nullptr;
     vec3 (*emitted)(const material*, float, float, const vec3&) = nullptr;
     vec3 (*value)(const texture*, float, float, const vec3&) = nullptr;
+    ray (*get_ray)(const camera*, float, float) = nullptr;
 };
 void set_device_bridge(const device_bridge& b);
 const device_bridge& get_device_bridge();

@@ -160,6 +160,11 @@ bvh_node::bvh_node(hitable** l, int n, float t0, float t1, inner_tag) : left(nul
     build(l, n);
 }
 
+ray camera::get_ray(float s, float t) const {
+    if (!rtnw::g_bridge.get_ray) rtnw::no_bridge("camera::get_ray");
+    return rtnw::g_bridge.get_ray(this, s, t);
+}
+
 // ---- camera, PSC/camera.h:21-39 ---------------------------------------------------------------------------------
 camera::camera(vec3 lookfrom, vec3 lookat, vec3 vup, float vfov, float aspect, float aperture, float focus_dist, float t0, float t1) {
     time0 = t0;

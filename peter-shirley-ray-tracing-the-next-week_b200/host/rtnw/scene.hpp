@@ -363,6 +363,7 @@ public:
     float len_radius, time0, time1;
     camera() {}
     camera(vec3 lookfrom, vec3 lookat, vec3 vup, float vfov, float aspect, float aperture, float focus_dist, float t0, float t1);
+    ray get_ray(float s, float t) const;  // PSC/camera.h:41-47; evaluated on the GPU like the other arithmetic entry points (device_bridge)
 };
 
 #endif  // RTNW_SCENE_HPP_

@@ -265,6 +265,23 @@ hitable* stress_shells() {
     return w.as_list();
 }
 
+// Not a reference scene: two bvh_nodes that are NEIGHBOURS in the top-level list (and a third after one sphere), so the
+// cooperative traversal enters a BVH item straight after leaving one (tests/test_gpu_parity.py).
+hitable* twin_bvh() {
+    pool w(4);
+    for (int part = 0; part < 3; ++part) {
+        pool g(40);
+        for (int k = 0; k < 40; ++k) {
+            const float x = -6.f + 0.3f * k + 0.05f * part, z = -3.f + 2.5f * part + 0.4f * (k % 5), r = 0.15f + 0.01f * (k % 7);
+            material* m = (k % 4 == 0) ? static_cast<material*>(new metal(vec3(0.8f, 0.7f, 0.6f), 0.1f)) : matte(0.3f + 0.01f * k, 0.4f, 0.2f + 0.2f * part);
+            g.add(new sphere(vec3(x, 0.2f + 0.1f * (k % 3), z), r, m));
+        }
+        if (part == 2) w.add(new sphere(vec3(0, -700, 0), 700, matte(0.5, 0.5, 0.5)));
+        w.add(new bvh_node(g.items, g.n, 0, 1));
+    }
+    return w.as_list();
+}
+
 hitable* wrap_in_bvh(hitable* flat_list, float t0, float t1) {
     hitable_list* l = static_cast<hitable_list*>(flat_list);
     return new bvh_node(l->list, l->list_size, t0, t1);

@@ -34,6 +34,7 @@ hitable* two_spheres();            // PSC/main.cpp:99-110
 hitable* earth();                  // PSC/main.cpp:87-97 with the synthetic RGB8 image
 hitable* earth(unsigned char* rgb, int nx, int ny);  // ... with a caller-supplied RGB8 image (decoded PNG)
 hitable* stress_shells();          // test fixture (not in the reference): 600 nested shells, every ray passes every box
+hitable* twin_bvh();               // test fixture: bvh_nodes that are neighbours in the top-level list
 hitable* wrap_in_bvh(hitable* flat_list, float t0, float t1);  // `new bvh_node(list->list, list->list_size, t0, t1)`
 
 // deterministic 1024x512 RGB8 stand-in for picture.png (the shipped PNG is RGBA and mis-strided)

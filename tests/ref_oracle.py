@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         L.ref_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]
         L.ref_scatter.restype = None
+        L.ref_epilogue.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_epilogue.restype = None
         _lib = L
     return _lib
 
@@ -71,8 +73,15 @@ VIEWS = {
 
 
 def view_of(name: str) -> dict:
-    v = dict(VIEWS[name.split("+")[0]])
+    base, _, snapshot = name.partition(":")
+    v = dict(VIEWS[base.split("+")[0]])
     v.update(focus_dist=10.0, time0=0.0, time1=1.0)
+    if snapshot in ("ch01", "ch03"):    # TNW/Chapter01_Motion Blur.cpp:16, TNW/Chapter03_Soild Texture.cpp:16
+        v.update(t_min=0.0, aperture=0.1, sky=1, emit=0, denan=0)
+    elif snapshot in ("ch07", "ch08"):  # TNW/Chapter07_Instance.cpp:25,173-178, TNW/Chapter08_Volume.cpp:26
+        v.update(t_min=0.01, aperture=0.1, lookfrom=(278, 278, -800), denan=0)
+    elif snapshot:
+        raise KeyError(snapshot)
     return v
 
 
@@ -81,7 +90,7 @@ class RefScene:
 
     def __init__(self, name: str, tagged: bool = True):
         self.name = name
-        self._h = lib().ref_scene_build(name.encode(), int(tagged))
+        self._h = lib().ref_scene_build(name.partition(":")[0].encode(), int(tagged))
         if not self._h:
             raise ValueError(f"unknown scene {name}")
 
@@ -161,3 +170,12 @@ def scatter(mat: np.ndarray, rays_in: np.ndarray, hits: np.ndarray, seed=1):
     lib().ref_scatter(mat.ctypes.data, rays_in.ctypes.data, hits.ctypes.data, n, seed, sc.ctypes.data, att.ctypes.data,
                       em.ctypes.data, flag.ctypes.data)
     return sc, att, em, flag
+
+
+def epilogue(sums: np.ndarray, ns: int, clamp255: bool = True) -> np.ndarray:
+    """PSC/main.cpp:315-325 (the reference's own lines) on (ny, nx, 3) float32 sums; returns (ny, nx, 3) int32, top row first"""
+    sums = np.ascontiguousarray(sums, dtype=np.float32)
+    ny, nx, _ = sums.shape
+    out = np.zeros((ny, nx, 3), dtype=np.int32)
+    lib().ref_epilogue(sums.ctypes.data, nx, ny, ns, int(clamp255), out.ctypes.data)
+    return out

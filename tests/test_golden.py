@@ -108,3 +108,36 @@ def test_cuda_reproduces_golden_units(rtnw, ctx):
     got = rtnw.camera_rays(ctx, cam, 200, 100, g["cam_ij"], g["cam_sample"], seed=77)
     for f in ("origin", "direction", "time", "key"):
         assert np.array_equal(got[f], g["cam_rays"][f]), f
+
+
+def _epilogue_cases():
+    g = np.load(GOLD / "epilogue.npz")
+    for ns in (1, 7, 10, 100, 1000):
+        yield ns, g[f"sums_{ns}"], g[f"clamped_{ns}"], g[f"raw_{ns}"]
+
+
+def test_host_epilogue_reproduces_the_references_own_lines(rtnw):
+    """rtnw_host_quantize against PSC/main.cpp:315-325 as compiled from the reference's own text (ref_epilogue in the
+    harness, committed as tests/golden/epilogue.npz): quantisation boundaries +-1 ulp, lights > 1, zero, huge, five ns"""
+    for ns, sums, clamped, raw in _epilogue_cases():
+        assert np.array_equal(rtnw.quantize(sums, ns, clamp255=True), clamped), ns
+        assert np.array_equal(rtnw.quantize(sums, ns, clamp255=False), raw), ns
+
+
+def test_epilogue_fixture_matches_the_live_reference():
+    import ref_oracle as ro
+    if not ro.available():
+        pytest.skip("compiled reference not present")
+    for ns, sums, clamped, raw in _epilogue_cases():
+        assert np.array_equal(ro.epilogue(sums, ns, True), clamped) and np.array_equal(ro.epilogue(sums, ns, False), raw)
+
+
+@pytest.mark.gpu
+def test_device_epilogue_reproduces_the_references_own_lines(rtnw, ctx):
+    """k_quantize (rtnw_quantize_device) bit for bit against the same fixture"""
+    import torch
+    for ns, sums, clamped, raw in _epilogue_cases():
+        ny, nx, _ = sums.shape
+        dev = torch.from_numpy(sums).cuda()
+        assert np.array_equal(ctx.quantize_device(dev.data_ptr(), nx, ny, ns, clamp255=True), clamped), ns
+        assert np.array_equal(ctx.quantize_device(dev.data_ptr(), nx, ny, ns, clamp255=False), raw), ns

@@ -1,18 +1,25 @@
 """Statistical image parity against the reference running on its own generator (glibc drand48): the GPU's samples are
-independent of the reference's, so the comparison is in distribution:
-  (i)   global mean radiance per channel within 1.5 % (+ 3 standard errors);
-  (ii)  >= 98.5 % of pixel channels with |mean_gpu - mean_ref| <= 4 * sqrt(var_ref/K + var_gpu/K), the variances estimated
-        from K = 8 independent batches on each side (a perfect match gives ~99.99 %; heavy-tailed pixels near the small
-        light make the batch variance itself noisy, hence the slack);
-  (iii) PSNR of the gamma-encoded 8-bit images (PSC/main.cpp:315-325) no worse than 1.5 dB below the noise floor, i.e.
-        the PSNR between two independent reference renders of the same sample count (second half of the fixture).
-The reference batches are committed fixtures (tests/golden/stat_*.npz, tests/golden/make_stat_golden.py)."""
+independent of the reference's, so the comparison is in distribution, with the bounds of SURVEY.md §8c, at 2048 spp
+(K = 8 batches of 256) and >= 100x100 pixels, on all five BASELINE configs' scenes:
+  (i)   global mean radiance per channel within 0.5 %;
+  (ii)  >= 99 % of pixel channels with |mean_gpu - mean_ref| <= 4 * sqrt(var_ref + var_gpu), the variances of the means
+        estimated from the K batch means on each side;
+  (iii) PSNR of the gamma-encoded 8-bit images (PSC/main.cpp:315-325) against the reference no worse than 1 dB below the
+        noise floor — the PSNR between the two independent reference halves A and B of the fixture (a CPU-vs-CPU rerun
+        with other srand48 seeds) — and above the absolute floor PSNR_FLOOR_DB stated per scene below.
+The same three criteria are applied to reference half B against half A (CPU only), which shows what an exact sampler
+scores.  Fixtures: tests/golden/stat_*.npz, generated from the compiled reference by tests/golden/make_stat_golden.py."""
 from pathlib import Path
 
 import numpy as np
 import pytest
 
 GOLD = Path(__file__).resolve().parent / "golden"
+SCENES = ["cornell_box", "cornell_smoke", "two_perlin", "final_northstar", "ch01_random"]
+# absolute floors: CPU-vs-CPU PSNR of the committed fixtures (A vs B at 2048 spp each) minus 1 dB, rounded down
+# (measured A vs B: 34.9 / 37.1 / 45.0 / 28.3 / 47.2 dB)
+PSNR_FLOOR_DB = {"cornell_box": 33.0, "cornell_smoke": 36.0, "two_perlin": 43.0, "final_northstar": 27.0, "ch01_random": 46.0}
+MEAN_TOL, Z_FRAC = 0.005, 0.99
 
 
 def _encode(mean):
@@ -24,42 +31,49 @@ def _psnr(a, b):
     return 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cornell_box", "final_northstar", "ch01_random"])
-def test_image_statistics_match_reference_drand48(rtnw, ctx, name):
+def _criteria(mean_x, var_x, mean_ref, var_ref):
+    """(worst relative global-mean error over the channels, fraction of pixel channels within 4 sigma, PSNR)"""
+    rel = max(abs(mean_x[..., c].mean() - mean_ref[..., c].mean()) / mean_ref[..., c].mean() for c in range(3))
+    se = np.sqrt(var_x + var_ref)
+    ok = se > 0
+    z = np.abs(mean_x - mean_ref)[ok] / se[ok]
+    return rel, float((z <= 4).mean()), _psnr(mean_x, mean_ref)
+
+
+def _load(name):
     g = np.load(GOLD / f"stat_{name}.npz")
-    nx, ny, spp, K = int(g["nx"]), int(g["ny"]), int(g["spp"]), int(g["k"])
-    ref_a, ref_b = g["batches"][:K].astype(np.float64), g["batches"][K:].astype(np.float64)
+    K = int(g["k"])
+    half = lambda t: (g[f"mean_{t}"].astype(np.float64), g[f"var_{t}"].astype(np.float64) / K)  # variance of the half's mean
+    return g, K, half("a"), half("b")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SCENES)
+def test_image_statistics_match_reference_drand48(rtnw, ctx, name):
+    g, K, (m_ref, v_ref), (m_b, _) = _load(name)
+    nx, ny, spp = int(g["nx"]), int(g["ny"]), int(g["spp"])
+    assert nx * ny >= 10000 and K * spp >= 2048
     hs = rtnw.HostScene(name)
     ds = ctx.upload(hs.desc_ptr)
     cam = hs.camera(nx, ny)
     gpu = np.stack([ds.render(cam, hs.params(nx=nx, ny=ny, ns=spp, seed=900 + k))[0] / spp for k in range(K)]).astype(np.float64)
     ds.close()
-    m_gpu, m_ref = gpu.mean(0), ref_a.mean(0)
-    se = np.sqrt(gpu.var(0, ddof=1) / K + ref_a.var(0, ddof=1) / K)
-    # (i) global means
-    for c in range(3):
-        gm, rm = m_gpu[..., c].mean(), m_ref[..., c].mean()
-        se_glob = np.sqrt((gpu[..., c].mean(axis=(1, 2)).var(ddof=1) + ref_a[..., c].mean(axis=(1, 2)).var(ddof=1)) / K)
-        assert abs(gm - rm) <= 0.015 * rm + 3 * se_glob, (name, c, gm, rm, se_glob)
-    # (ii) per-pixel z-scores
-    z = np.abs(m_gpu - m_ref) / np.maximum(se, 1e-9)
-    frac = (z[se > 0] <= 4).mean()
-    assert frac >= 0.985, f"{name}: only {frac:.4f} of pixel channels within 4 sigma"
-    # (iii) PSNR against the noise floor of the reference itself
-    floor = _psnr(ref_b.mean(0), m_ref)
-    got = _psnr(m_gpu, m_ref)
-    assert got >= floor - 1.5, f"{name}: PSNR {got:.2f} dB vs reference-vs-reference {floor:.2f} dB"
+    rel, frac, psnr = _criteria(gpu.mean(0), gpu.var(0, ddof=1) / K, m_ref, v_ref)
+    floor = _psnr(m_b, m_ref)
+    print(f"{name}: global mean off by {100 * rel:.3f} %, {100 * frac:.3f} % of pixel channels within 4 sigma, "
+          f"PSNR {psnr:.2f} dB (reference vs reference {floor:.2f} dB)")
+    assert rel <= MEAN_TOL, f"{name}: global mean radiance off by {100 * rel:.3f} %"
+    assert frac >= Z_FRAC, f"{name}: only {frac:.4f} of pixel channels within 4 sigma"
+    assert psnr >= floor - 1.0 and psnr >= PSNR_FLOOR_DB[name], f"{name}: PSNR {psnr:.2f} dB vs reference-vs-reference {floor:.2f} dB"
 
 
-def test_fixtures_are_self_consistent():
-    """the two halves of each fixture are two independent reference renders: their difference defines the noise floor and
-    must itself pass the z-score criterion (guards the test's statistics, CPU only)"""
-    for name in ["cornell_box", "final_northstar", "ch01_random"]:
-        g = np.load(GOLD / f"stat_{name}.npz")
-        K = int(g["k"])
-        a, b = g["batches"][:K].astype(np.float64), g["batches"][K:].astype(np.float64)
-        se = np.sqrt(a.var(0, ddof=1) / K + b.var(0, ddof=1) / K)
-        z = np.abs(a.mean(0) - b.mean(0)) / np.maximum(se, 1e-9)
-        assert (z[se > 0] <= 4).mean() >= 0.985
-        assert _psnr(a.mean(0), b.mean(0)) > 10
+@pytest.mark.parametrize("name", SCENES)
+def test_reference_rerun_meets_the_same_bounds(name):
+    """CPU-vs-CPU: the second reference half against the first under the same criteria (guards the statistics, states the
+    noise floor the absolute PSNR bounds come from)"""
+    g, K, (m_a, v_a), (m_b, v_b) = _load(name)
+    rel, frac, psnr = _criteria(m_b, v_b, m_a, v_a)
+    assert rel <= MEAN_TOL and frac >= Z_FRAC, (name, rel, frac)
+    assert psnr - 1.0 >= PSNR_FLOOR_DB[name] > 0, (name, psnr)
+    ga, gb = g["glob_a"], g["glob_b"]  # the global means' own standard error is far below the 0.5 % bound
+    assert np.all(np.sqrt(ga.var(0, ddof=1) / K + gb.var(0, ddof=1) / K) / ga.mean(0) < 0.002)
