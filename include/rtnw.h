@@ -231,6 +231,16 @@ int rtnw_measure_fp32_peak(rtnw_ctx* ctx, float* tflops);
 
 int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out);
 
+/* rtnw_scene_upload in two steps, for callers that upload the same scene repeatedly or to several devices: rtnw_scene_prepare
+ * turns the tables into the device image once on the host (validation, record stream, gate tree — no device needed; the image
+ * lives in pinned memory when a CUDA driver is present), rtnw_scene_upload_prepared is then one host->device copy of it.
+ * rtnw_scene_upload(ctx, desc) == prepare + upload_prepared + free. */
+typedef struct rtnw_prepared rtnw_prepared;
+int rtnw_scene_prepare(const rtnw_scene_desc* desc, rtnw_prepared** out);
+int64_t rtnw_prepared_bytes(const rtnw_prepared* p);   /* size of the device image = bytes one upload copies */
+int rtnw_scene_upload_prepared(rtnw_ctx* ctx, const rtnw_prepared* prepared, rtnw_scene** out);
+int rtnw_prepared_free(rtnw_prepared* p);
+
 /* The device tables rtnw_scene_upload derives from `desc`, built on the host WITHOUT a device and copied out for
  * inspection (the invariants the traversal's exactness rests on are checked on the CPU from these, tests/test_device_tables.py).
  * table: 0 = record stream (32 B each: 8 floats, [6] = tag bits, [7] = int), 1 = per-record leaf id (int32),

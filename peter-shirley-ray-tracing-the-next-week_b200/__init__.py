@@ -114,7 +114,8 @@ DEVICE_SYMBOLS = ["rtnw_last_error", "rtnw_abi_version", "rtnw_device_count", "r
                   "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_quantize_device", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
                   "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays", "rtnw_camera_get_rays", "rtnw_plan_sample_ranges",
                   "rtnw_scene_inspect", "rtnw_ctx_create_multi", "rtnw_ctx_destroy_multi", "rtnw_multi_device_count",
-                  "rtnw_scene_upload_multi", "rtnw_scene_free_multi", "rtnw_render_multi"]
+                  "rtnw_scene_upload_multi", "rtnw_scene_free_multi", "rtnw_render_multi", "rtnw_scene_prepare", "rtnw_prepared_bytes",
+                  "rtnw_scene_upload_prepared", "rtnw_prepared_free"]
 HOST_SYMBOLS = ["rtnw_host_last_error", "rtnw_host_scene_build", "rtnw_host_scene_free", "rtnw_host_scene_desc",
                 "rtnw_host_scene_leaf_count", "rtnw_host_scene_camera", "rtnw_host_scene_view", "rtnw_host_make_camera",
                 "rtnw_host_quantize", "rtnw_host_write_ppm", "rtnw_host_load_png", "rtnw_host_free_image"]
@@ -189,6 +190,11 @@ def device_lib() -> C.CDLL:
         L.rtnw_camera_rays.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
                                        C.c_uint64, C.c_void_p]
         L.rtnw_camera_get_rays.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.rtnw_scene_prepare.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+        L.rtnw_prepared_bytes.argtypes = [C.c_void_p]
+        L.rtnw_prepared_bytes.restype = C.c_int64
+        L.rtnw_scene_upload_prepared.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rtnw_prepared_free.argtypes = [C.c_void_p]
         L.rtnw_ctx_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         L.rtnw_ctx_destroy_multi.argtypes = [C.c_void_p]
         L.rtnw_multi_device_count.argtypes = [C.c_void_p]
@@ -347,12 +353,39 @@ class Context:
             pass
 
 
+class PreparedScene:
+    """The device image of a scene_desc built once on the host (rtnw_scene_prepare); upload it with Context.upload()."""
+
+    def __init__(self, desc):
+        self._h = C.c_void_p()
+        ptr = desc if isinstance(desc, C.POINTER(SceneDesc)) else C.pointer(desc)
+        _check_dev(device_lib().rtnw_scene_prepare(ptr, C.byref(self._h)))
+
+    @property
+    def nbytes(self) -> int:
+        return int(device_lib().rtnw_prepared_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            device_lib().rtnw_prepared_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceScene:
     """Device-resident copy of a scene_desc (rtnw_scene)."""
 
     def __init__(self, ctx: Context, desc):
         self.ctx = ctx
         self._h = C.c_void_p()
+        if isinstance(desc, PreparedScene):
+            _check_dev(device_lib().rtnw_scene_upload_prepared(ctx._h, desc._h, C.byref(self._h)))
+            return
         ptr = desc if isinstance(desc, C.POINTER(SceneDesc)) else C.pointer(desc)
         _check_dev(device_lib().rtnw_scene_upload(ctx._h, ptr, C.byref(self._h)))
 

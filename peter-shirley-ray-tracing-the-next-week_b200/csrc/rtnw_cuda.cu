@@ -1116,12 +1116,27 @@ int64_t rtnw_scene_inspect(const rtnw_scene_desc* desc, int32_t table, void* buf
     return (int64_t)bytes;
 }
 
-int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out) {
+// The device image of a scene, built once on the host (no device needed): one slab with every table at a 256-byte
+// aligned offset, in pinned memory when a CUDA driver is present (so an upload is a single asynchronous DMA).
+struct rtnw_prepared {
+    uint8_t* host = nullptr;
+    bool pinned = false;
+    size_t bytes = 0;
+    size_t o_recs = 0, o_leaf = 0, o_rxf = 0, o_nodes = 0, o_gates = 0, o_xf = 0, o_mat = 0, o_tex = 0, o_rv = 0, o_perm = 0, o_img = 0;
+    int32_t n_recs = 0, n_materials = 0, n_textures = 0;
+};
+
+int rtnw_prepared_free(rtnw_prepared* p) {
+    if (!p) return RTNW_OK;
+    if (p->host) { if (p->pinned) cudaFreeHost(p->host); else std::free(p->host); }
+    delete p;
+    return RTNW_OK;
+}
+
+int rtnw_scene_prepare(const rtnw_scene_desc* desc, rtnw_prepared** out) {
     if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
     *out = nullptr;
     if (!desc) return fail(RTNW_ERR_INVALID, "null scene_desc");
-    int rc = check_ctx(ctx);
-    if (rc != RTNW_OK) return rc;
     stream_builder sb(*desc);
     if (!sb.run()) return fail(RTNW_ERR_INVALID, "scene_desc: " + sb.err);
 
@@ -1136,36 +1151,57 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
     }
 
     // one slab, every table 256-byte aligned
+    rtnw_prepared* P = new rtnw_prepared();
     const size_t sz_recs = sb.recs.size() * sizeof(rec), sz_leaf = sb.leaf.size() * sizeof(int32_t);
     const size_t sz_xf = (size_t)desc->n_xform_ops * sizeof(rtnw_xform_op);
     const size_t sz_mat = (size_t)desc->n_materials * sizeof(rtnw_material), sz_tex = (size_t)desc->n_textures * sizeof(rtnw_texture);
     const size_t sz_img = (size_t)desc->image_bytes, sz_rv = 256 * sizeof(float4), sz_perm = 768;
-    size_t off = 0;
-    const size_t o_recs = off; off += align256(sz_recs);
-    const size_t o_leaf = off; off += align256(sz_leaf);
-    const size_t o_rxf = off; off += align256(sz_leaf);
     const size_t sz_nodes = sb.wnodes.size() * sizeof(float4), sz_gates = sb.gate_leaves.size() * sizeof(int2);
-    const size_t o_nodes = off; off += align256(sz_nodes);
-    const size_t o_gates = off; off += align256(sz_gates);
-    const size_t o_xf = off; off += align256(sz_xf);
-    const size_t o_mat = off; off += align256(sz_mat);
-    const size_t o_tex = off; off += align256(sz_tex);
-    const size_t o_rv = off; off += align256(sz_rv);
-    const size_t o_perm = off; off += align256(sz_perm);
-    const size_t o_img = off; off += align256(sz_img + 16);
-    std::vector<uint8_t> host(off, 0);
-    std::memcpy(host.data() + o_recs, sb.recs.data(), sz_recs);
-    std::memcpy(host.data() + o_leaf, sb.leaf.data(), sz_leaf);
-    std::memcpy(host.data() + o_rxf, sb.rec_xf.data(), sz_leaf);
-    std::memcpy(host.data() + o_nodes, sb.wnodes.data(), sz_nodes);
-    std::memcpy(host.data() + o_gates, sb.gate_leaves.data(), sz_gates);
-    std::memcpy(host.data() + o_xf, desc->xforms, sz_xf);
-    if (sz_mat) std::memcpy(host.data() + o_mat, desc->materials, sz_mat);
-    if (sz_tex) std::memcpy(host.data() + o_tex, desc->textures, sz_tex);
-    std::memcpy(host.data() + o_rv, ranvec.data(), sz_rv);
-    std::memcpy(host.data() + o_perm, perm.data(), sz_perm);
-    if (sz_img) std::memcpy(host.data() + o_img, desc->images, sz_img);
+    size_t off = 0;
+    P->o_recs = off; off += align256(sz_recs);
+    P->o_leaf = off; off += align256(sz_leaf);
+    P->o_rxf = off; off += align256(sz_leaf);
+    P->o_nodes = off; off += align256(sz_nodes);
+    P->o_gates = off; off += align256(sz_gates);
+    P->o_xf = off; off += align256(sz_xf);
+    P->o_mat = off; off += align256(sz_mat);
+    P->o_tex = off; off += align256(sz_tex);
+    P->o_rv = off; off += align256(sz_rv);
+    P->o_perm = off; off += align256(sz_perm);
+    P->o_img = off; off += align256(sz_img + 16);
+    P->bytes = off;
+    void* pin = nullptr;
+    if (cudaHostAlloc(&pin, off, cudaHostAllocDefault) == cudaSuccess) { P->host = static_cast<uint8_t*>(pin); P->pinned = true; }
+    else { cudaGetLastError(); P->host = static_cast<uint8_t*>(std::malloc(off)); }
+    if (!P->host) { delete P; return fail(RTNW_ERR_NOMEM, "cannot allocate the host image of the scene"); }
+    std::memset(P->host, 0, off);
+    std::memcpy(P->host + P->o_recs, sb.recs.data(), sz_recs);
+    std::memcpy(P->host + P->o_leaf, sb.leaf.data(), sz_leaf);
+    std::memcpy(P->host + P->o_rxf, sb.rec_xf.data(), sz_leaf);
+    std::memcpy(P->host + P->o_nodes, sb.wnodes.data(), sz_nodes);
+    std::memcpy(P->host + P->o_gates, sb.gate_leaves.data(), sz_gates);
+    std::memcpy(P->host + P->o_xf, desc->xforms, sz_xf);
+    if (sz_mat) std::memcpy(P->host + P->o_mat, desc->materials, sz_mat);
+    if (sz_tex) std::memcpy(P->host + P->o_tex, desc->textures, sz_tex);
+    std::memcpy(P->host + P->o_rv, ranvec.data(), sz_rv);
+    std::memcpy(P->host + P->o_perm, perm.data(), sz_perm);
+    if (sz_img) std::memcpy(P->host + P->o_img, desc->images, sz_img);
+    P->n_recs = (int32_t)sb.recs.size();
+    P->n_materials = desc->n_materials;
+    P->n_textures = desc->n_textures;
+    *out = P;
+    return RTNW_OK;
+}
 
+int64_t rtnw_prepared_bytes(const rtnw_prepared* p) { return p ? (int64_t)p->bytes : 0; }
+
+int rtnw_scene_upload_prepared(rtnw_ctx* ctx, const rtnw_prepared* P, rtnw_scene** out) {
+    if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (!P) return fail(RTNW_ERR_INVALID, "null prepared scene");
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    const size_t off = P->bytes;
     rtnw_scene* s = new rtnw_scene();
     cudaError_t e = cudaSuccess;
     for (int q = 0; q < 2 && !s->slab; ++q)
@@ -1179,7 +1215,8 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
         e = cudaMalloc(&s->slab, off);
         s->slab_bytes = off;
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->slab, host.data(), off, cudaMemcpyHostToDevice, ctx->stream);
+    // stream-ordered: the next render on this context's stream (or a stream ordered after it) sees the tables
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->slab, P->host, off, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         if (s->slab) cudaFree(s->slab);
@@ -1187,22 +1224,35 @@ int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** o
         return fail(e == cudaErrorMemoryAllocation ? RTNW_ERR_NOMEM : RTNW_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
     }
     uint8_t* base = static_cast<uint8_t*>(s->slab);
-    s->view.recs = reinterpret_cast<const rec*>(base + o_recs);
-    s->view.rec_leaf = reinterpret_cast<const int32_t*>(base + o_leaf);
-    s->view.rec_xf = reinterpret_cast<const uint32_t*>(base + o_rxf);
-    s->view.wnodes = reinterpret_cast<const float4*>(base + o_nodes);
-    s->view.gates = reinterpret_cast<const int2*>(base + o_gates);
-    s->view.xforms = reinterpret_cast<const rtnw_xform_op*>(base + o_xf);
-    s->view.materials = reinterpret_cast<const rtnw_material*>(base + o_mat);
-    s->view.textures = reinterpret_cast<const rtnw_texture*>(base + o_tex);
-    s->view.ranvec = reinterpret_cast<const float4*>(base + o_rv);
-    s->view.perm = base + o_perm;
-    s->view.images = base + o_img;
-    s->view.n_recs = (int32_t)sb.recs.size();
-    s->view.n_materials = desc->n_materials;
-    s->view.n_textures = desc->n_textures;
+    s->view.recs = reinterpret_cast<const rec*>(base + P->o_recs);
+    s->view.rec_leaf = reinterpret_cast<const int32_t*>(base + P->o_leaf);
+    s->view.rec_xf = reinterpret_cast<const uint32_t*>(base + P->o_rxf);
+    s->view.wnodes = reinterpret_cast<const float4*>(base + P->o_nodes);
+    s->view.gates = reinterpret_cast<const int2*>(base + P->o_gates);
+    s->view.xforms = reinterpret_cast<const rtnw_xform_op*>(base + P->o_xf);
+    s->view.materials = reinterpret_cast<const rtnw_material*>(base + P->o_mat);
+    s->view.textures = reinterpret_cast<const rtnw_texture*>(base + P->o_tex);
+    s->view.ranvec = reinterpret_cast<const float4*>(base + P->o_rv);
+    s->view.perm = base + P->o_perm;
+    s->view.images = base + P->o_img;
+    s->view.n_recs = P->n_recs;
+    s->view.n_materials = P->n_materials;
+    s->view.n_textures = P->n_textures;
     *out = s;
     return RTNW_OK;
+}
+
+int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out) {
+    if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    rtnw_prepared* P = nullptr;
+    if ((rc = rtnw_scene_prepare(desc, &P)) != RTNW_OK) return rc;
+    rc = rtnw_scene_upload_prepared(ctx, P, out);
+    const std::string msg = g_err;
+    rtnw_prepared_free(P);
+    return rc == RTNW_OK ? RTNW_OK : fail(rc, msg);
 }
 
 int rtnw_scene_free(rtnw_ctx* ctx, rtnw_scene* scene) {
@@ -1485,12 +1535,16 @@ int rtnw_scene_upload_multi(rtnw_multi* m, const rtnw_scene_desc* desc, rtnw_mul
     if (!out) return fail(RTNW_ERR_INVALID, "null out pointer");
     *out = nullptr;
     if (!m) return fail(RTNW_ERR_INVALID, "null context");
+    rtnw_prepared* P = nullptr;  // the device image is built once, then copied to every device
+    int rc = rtnw_scene_prepare(desc, &P);
+    if (rc != RTNW_OK) return rc;
     rtnw_multi_scene* ms = new rtnw_multi_scene();
     ms->n = m->n;
     for (int d = 0; d < m->n; ++d) {
-        const int rc = rtnw_scene_upload(m->ctx[d], desc, &ms->scene[d]);
-        if (rc != RTNW_OK) { const std::string msg = g_err; rtnw_scene_free_multi(m, ms); return fail(rc, msg); }
+        rc = rtnw_scene_upload_prepared(m->ctx[d], P, &ms->scene[d]);
+        if (rc != RTNW_OK) { const std::string msg = g_err; rtnw_scene_free_multi(m, ms); rtnw_prepared_free(P); return fail(rc, msg); }
     }
+    rtnw_prepared_free(P);
     *out = ms;
     return RTNW_OK;
 }
