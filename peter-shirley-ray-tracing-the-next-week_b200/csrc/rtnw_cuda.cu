@@ -535,11 +535,44 @@ struct stream_builder {
 
     // Append the records of prim slots [first, first+count).  first_cont: narrowing flag of the first primitive;
     // the following primitives of the range always continue its scope (list semantics).
-    bool emit_prims(int32_t first, int32_t count, bool first_cont, bool boundary) {
+    // class of a prim slot for the run-specialised list scan (scan_run): 1 plain sphere, 2 plain moving sphere, 3 plain box, 0 other
+    int run_class(int32_t s, int32_t end) const {
+        const rtnw_prim& p = d.prims[s];
+        if (RTNW_KX_XFORM(p.kx) != 0) return 0;
+        switch (RTNW_KX_KIND(p.kx)) {
+            case RTNW_PRIM_SPHERE: return 1;
+            case RTNW_PRIM_MOVING_SPHERE: return (s + 1 < end && RTNW_KX_KIND(d.prims[s + 1].kx) == RTNW_PRIM_EXT) ? 2 : 0;
+            case RTNW_PRIM_BOX: return 3;
+            default: return 0;
+        }
+    }
+    static constexpr int MIN_RUN = 8;  // primitives; shorter runs stay in the generic scan
+
+    bool emit_prims(int32_t first, int32_t count, bool first_cont, bool boundary, bool allow_runs = false) {
         if (first < 0 || count < 0 || count > d.n_prim_slots - first) return bad("primitive range out of bounds");
         bool cont = first_cont;
         size_t last_head = (size_t)-1;  // the record a leaf scan tests last (a moving sphere / medium head, not its trailing records)
+        int32_t run_end = first;        // slots below this one already belong to a run that has its header
         for (int32_t s = first; s < first + count; ++s) {
+            if (allow_runs && s >= run_end) {  // does a run of plain spheres / (moving) spheres / boxes start here?
+                const int c0 = run_class(s, first + count);
+                if (c0) {
+                    const bool sph = c0 <= 2;
+                    bool pure = c0 == 1;
+                    int32_t q = s, prims = 0, nrec = 0;
+                    while (q < first + count) {
+                        const int c = run_class(q, first + count);
+                        if (!c || (c <= 2) != sph) break;
+                        pure = pure && c == 1;
+                        ++prims; nrec += c == 2 ? 2 : 1; q += c == 2 ? 2 : 1;
+                    }
+                    if (prims >= MIN_RUN) {
+                        const uint32_t k = sph ? (pure ? K_RUN_SPHERE : K_RUN_SPHERELIKE) : K_RUN_BOX;
+                        push(make_float4(bits(nrec), 0, 0, 0), 0, 0, RTNW_TAG(k, 0, 1, 0), 0, -1);
+                    }
+                    run_end = q;  // (short runs are not examined again)
+                }
+            }
             last_head = recs.size();
             const rtnw_prim& p = d.prims[s];
             const uint32_t kind = RTNW_KX_KIND(p.kx), flip = RTNW_KX_FLIP(p.kx), chain = RTNW_KX_XFORM(p.kx);
@@ -780,7 +813,7 @@ struct stream_builder {
             const size_t at = recs.size();
             push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_ITEM, 0, 0, it.xform), (int32_t)it.kind, -1);
             if (it.kind == RTNW_ITEM_PRIMS) {
-                if (!emit_prims(it.first, it.count, true, false)) return false;
+                if (!emit_prims(it.first, it.count, true, false, /*allow_runs=*/true)) return false;
             } else if (it.kind == RTNW_ITEM_BVH) {
                 int wroot = 0, wdepth = 0;
                 if (!emit_bvh_item(it, wroot, wdepth)) return false;  // leaves -> record stream, gates + gate tree -> side tables

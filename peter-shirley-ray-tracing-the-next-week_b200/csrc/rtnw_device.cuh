@@ -33,7 +33,10 @@ namespace rtnw_dev {
 // ------------------------------------------------------------------------------------------------ records
 enum rec_kind : uint32_t {
     K_SPHERE = 0, K_MSPHERE = 1, K_RECT_XY = 2, K_RECT_XZ = 3, K_RECT_YZ = 4, K_BOX = 5, K_MEDIUM = 6, K_EXT = 7,
-    K_NODE = 8, K_ITEM = 9, K_END = 10
+    K_NODE = 8, K_ITEM = 9, K_END = 10,
+    // run headers inside a list item (scan_run): the next a.x records are plain spheres / plain (moving) spheres / plain boxes
+    // without a transform chain, scanned by a loop specialised for them — same records, same order, same narrowing
+    K_RUN_SPHERE = 11, K_RUN_SPHERELIKE = 12, K_RUN_BOX = 13
 };
 #define RTNW_TAG_FLIP 16u
 #define RTNW_TAG_CONT 32u  // same narrowing scope as the previous primitive (list semantics, PSC/hitable_list.h:23-29)
@@ -437,6 +440,49 @@ __device__ unsigned long long g_round_stats[32];
 #else
 #define RTNW_STAT(i, v) ((void)0)
 #endif
+
+// A run of same-kind plain records inside a list item (hitable_list::hit, PSC/hitable_list.h:20-32): the generic scan spends
+// ~50 of its ~80 instructions per primitive on record decode, the kind switch and loop bookkeeping; all lanes of a warp
+// scan the same record, so a loop that knows the kind needs one 128-bit load and the arithmetic of the test itself.
+// Order, narrowing limit and the key of an accepted hit are exactly those of the generic scan.
+template <bool COUNT, int RUN>
+__device__ __forceinline__ void scan_run(const scene_view& S, int first, int nrec, const ray_t& r, float a, float t_min, float& lim,
+                                         hkey_t& key, trav_counters& cnt) {
+    const int end = first + nrec;
+    if (RUN == K_RUN_SPHERE) {  // PSC/sphere.h:25-52, one record each
+#pragma unroll 4
+        for (int j = first; j < end; ++j) {
+            const float4 A = __ldg(&S.recs[j].a);
+            float t;
+            if (hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
+        }
+        if (COUNT) cnt.prim_tests += nrec;
+    } else if (RUN == K_RUN_SPHERELIKE) {  // spheres and moving spheres mixed (PSC/sphere.h:92-118: two records); the kind test is warp-uniform
+#pragma unroll 1
+        for (int j = first; j < end;) {
+            const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
+            f3 c = mk3(A.x, A.y, A.z);
+            int step = 1;
+            if ((__float_as_uint(B.z) & 15u) == K_MSPHERE) {
+                const float4 A2 = __ldg(&S.recs[j + 1].a);
+                c = moving_center(c, mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
+                step = 2;
+            }
+            if (COUNT) cnt.prim_tests++;
+            float t;
+            if (hit_sphere(c, A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
+            j += step;
+        }
+    } else {  // K_RUN_BOX, PSC/box.h:23-38
+#pragma unroll 2
+        for (int j = first; j < end; ++j) {
+            const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
+            float t; int face = 0;
+            if (hit_box(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, t_min, lim, t, face)) { lim = t; key = make_key(t, j, face); }
+        }
+        if (COUNT) cnt.prim_tests += nrec;
+    }
+}
 
 // ---- block-cooperative closest hit --------------------------------------------------------------------------
 // Every thread of the block owns one ray (or none).  All rays walk the same record stream, item by item:
@@ -925,6 +971,15 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_sme
 #pragma unroll 1
             for (int j = i + 1; j < next;) {
                 const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
+                const uint32_t rk = __float_as_uint(B.z) & 15u;
+                if (rk >= K_RUN_SPHERE) {  // a run header (uniform over the block): the specialised loop takes the next A.x records
+                    const int nrec = __float_as_int(A.x);
+                    if (rk == K_RUN_SPHERE) scan_run<COUNT, K_RUN_SPHERE>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
+                    else if (rk == K_RUN_SPHERELIKE) scan_run<COUNT, K_RUN_SPHERELIKE>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
+                    else scan_run<COUNT, K_RUN_BOX>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
+                    j += 1 + nrec;
+                    continue;
+                }
                 bool hit; float t; int face;
                 const int step = test_record<COUNT>(S, j, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
                 if (hit) { lim = t; key = make_key(t, j, face); }  // list narrowing: an accepted hit is the new closest
