@@ -115,9 +115,12 @@ enum rtnw_texture_kind {
     RTNW_TEX_NOISE = 2,    /* PSC/texture.h:47-59   c[0] = scale */
     RTNW_TEX_IMAGE = 3     /* PSC/surface_texture.h i0 = byte offset into the image pool, i1 = nx, i2 = ny (RGB8) */
 };
+/* rtnw_texture.flags of an image texture: sample the four texels around (u, v) and blend them (texel centres at i + 0.5, edges
+ * clamped) instead of the reference's nearest-texel lookup (PSC/surface_texture.h:19-30).  Not in the reference: an option. */
+#define RTNW_TEXF_BILINEAR 1u
 typedef struct rtnw_texture {
     uint32_t kind; int32_t i0, i1, i2;
-    float c[3]; uint32_t pad;
+    float c[3]; uint32_t flags;
 } rtnw_texture; /* 32 B */
 
 /* Borrowed host pointers; rtnw_scene_upload copies everything, the caller may free afterwards. */

@@ -420,6 +420,22 @@ static vec3 texture_value(const rtnw_scene_desc* d, int tex, float u, float v, v
         default: {
             const int nx = t->i1, ny = t->i2;
             const uint8_t* data = d->images + t->i0;
+            if (t->flags & RTNW_TEXF_BILINEAR) { /* this framework's option, not in the reference: same float32 steps as the device */
+                const float fx = (1.f - u) * (float)nx - 0.5f, fy = (1.f - v) * (float)ny - 0.5f;
+                const float x0 = floorf(fx), y0 = floorf(fy);
+                const float wx = fx - x0, wy = fy - y0;
+                int ii[4], jj[4];
+                ii[0] = ii[2] = (int)x0; ii[1] = ii[3] = (int)x0 + 1;
+                jj[0] = jj[1] = (int)y0; jj[2] = jj[3] = (int)y0 + 1;
+                vec3 c[4];
+                for (int q = 0; q < 4; ++q) {
+                    const int a = ii[q] < 0 ? 0 : (ii[q] > nx - 1 ? nx - 1 : ii[q]), b = jj[q] < 0 ? 0 : (jj[q] > ny - 1 ? ny - 1 : jj[q]);
+                    const uint8_t* px = data + 3 * a + 3 * nx * b;
+                    c[q] = V((float)px[0] / 255.0f, (float)px[1] / 255.0f, (float)px[2] / 255.0f);
+                }
+                const vec3 top = vadd(smul(1.f - wx, c[0]), smul(wx, c[1])), bot = vadd(smul(1.f - wx, c[2]), smul(wx, c[3]));
+                return vadd(smul(1.f - wy, top), smul(wy, bot));
+            }
             int i = (1 - u) * nx;
             int j = (1 - v) * ny - 0.001;
             if (i < 0) i = 0;

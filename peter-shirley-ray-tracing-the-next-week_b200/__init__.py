@@ -25,6 +25,7 @@ RTNW_ABI_VERSION = 5
 RTNW_OK = 0
 RTNW_ERR_INVALID, RTNW_ERR_CUDA, RTNW_ERR_UNSUPPORTED, RTNW_ERR_NOMEM = -1, -2, -3, -4
 BG_BLACK, BG_SKY = 0, 1
+TEXF_BILINEAR = 1
 F_DE_NAN, F_EMIT, F_FAST_BVH, F_COUNTERS, F_ACCUMULATE, F_ROTATE_SAMPLES = 1, 2, 4, 8, 16, 32
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -61,7 +62,7 @@ class Material(C.Structure):
 
 class Texture(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("i0", C.c_int32), ("i1", C.c_int32), ("i2", C.c_int32),
-                ("c", C.c_float * 3), ("pad", C.c_uint32)]
+                ("c", C.c_float * 3), ("flags", C.c_uint32)]
 
 
 class SceneDesc(C.Structure):

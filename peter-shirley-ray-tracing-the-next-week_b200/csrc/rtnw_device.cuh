@@ -1127,6 +1127,22 @@ __device__ __forceinline__ f3 texture_value(const scene_view& S, int tex, float 
         }
         // image: nearest texel, flipped u and v
         const int off = __float_as_int(t0.y), nx = __float_as_int(t0.z), ny = __float_as_int(t0.w);
+        if (__float_as_uint(t1.w) & RTNW_TEXF_BILINEAR) {  // option (not in the reference): blend the four texels around (u, v)
+            const float fx = (1.f - u) * (float)nx - 0.5f, fy = (1.f - v) * (float)ny - 0.5f;
+            const float x0 = floorf(fx), y0 = floorf(fy);
+            const float wx = fx - x0, wy = fy - y0;
+            const int i0 = min(max((int)x0, 0), nx - 1), i1 = min(max((int)x0 + 1, 0), nx - 1);
+            const int j0 = min(max((int)y0, 0), ny - 1), j1 = min(max((int)y0 + 1, 0), ny - 1);
+            f3 c[4];
+            const int ii[4] = {i0, i1, i0, i1}, jj[4] = {j0, j0, j1, j1};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint8_t* px = S.images + off + 3 * ii[q] + 3 * nx * jj[q];
+                c[q] = mk3((float)__ldg(px) / 255.0f, (float)__ldg(px + 1) / 255.0f, (float)__ldg(px + 2) / 255.0f);
+            }
+            const f3 top = (1.f - wx) * c[0] + wx * c[1], bot = (1.f - wx) * c[2] + wx * c[3];
+            return (1.f - wy) * top + wy * bot;
+        }
         int i = (int)((1.f - u) * (float)nx);
         int j = (int)((double)((1.f - v) * (float)ny) - 0.001);
         if (i < 0) i = 0;

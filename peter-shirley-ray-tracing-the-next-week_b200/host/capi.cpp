@@ -62,6 +62,15 @@ int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
     else if (name == "simple_light") { world = simple_light(); v = view_two_perlin(); v.sky = false; v.emit = true; }
     else if (name == "two_spheres") { world = two_spheres(); v = view_cornell(); v.sky = true; }
     else if (name == "earth") { world = earth(); v = view_cornell(); }
+    else if (name == "earth_bilinear") {  // earth() with the bilinear option of image_texture (not a reference scene)
+        int tx = 0, ty = 0;
+        unsigned char* tex = synthetic_earth(tx, ty);
+        hitable** l = new hitable*[2];
+        l[0] = new xz_rect(63, 483, 55, 482, 554, new diffuse_light(new constant_texture(vec3(7, 7, 7))));
+        l[1] = new sphere(vec3(360, 250, 150), 100, new lambertian(new image_texture(tex, tx, ty, true)));
+        world = new hitable_list(l, 2);
+        v = view_cornell();
+    }
     else if (name.rfind("earth@", 0) == 0) {  // earth() with its texture decoded from a PNG file, PSC/main.cpp:87-97
         int tx = 0, ty = 0;
         std::string err;

@@ -141,6 +141,7 @@ private:
                     S.images.insert(S.images.end(), im->data, im->data + (size_t)im->nx * im->ny * 3);
                     found = image_offset_.insert(std::make_pair(im->data, (int32_t)off)).first;
                 }
+                rec.flags = im->bilinear ? RTNW_TEXF_BILINEAR : 0u;
                 rec.i0 = found->second;
                 rec.i1 = im->nx;
                 rec.i2 = im->ny;

@@ -153,8 +153,9 @@ class image_texture : public texture {  // PSC/surface_texture.h:10-30, tightly 
 public:
     unsigned char* data;
     int nx, ny;
-    image_texture() : data(nullptr), nx(0), ny(0) {}
-    image_texture(unsigned char* pixels, int A, int B) : data(pixels), nx(A), ny(B) {}
+    bool bilinear;  // option of this framework (RTNW_TEXF_BILINEAR); the reference's lookup is nearest-texel
+    image_texture() : data(nullptr), nx(0), ny(0), bilinear(false) {}
+    image_texture(unsigned char* pixels, int A, int B, bool blend = false) : data(pixels), nx(A), ny(B), bilinear(blend) {}
     rtnw::tex_kind rtnw_kind() const override { return rtnw::tex_kind::image; }
 };
 

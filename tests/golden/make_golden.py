@@ -19,24 +19,30 @@ import ref_oracle as ro  # noqa: E402
 from raysets import FLT_MAX, make_rays  # noqa: E402
 
 TRACE = ["ch01_random", "two_perlin", "cornell_box", "cornell_smoke", "final", "final+bvh", "final_northstar", "earth",
-         "simple_light", "cornell_smoke+bvh", "random_scene+bvh", "test"]
+         "simple_light", "cornell_smoke+bvh", "random_scene+bvh", "test", "two_spheres"]
 RENDER = [("ch01_random", 32, 16, 4), ("two_perlin", 32, 16, 4), ("cornell_box", 24, 24, 6), ("cornell_smoke", 24, 24, 6),
-          ("final", 20, 20, 2), ("final+bvh", 24, 24, 3), ("final_northstar", 48, 48, 4), ("simple_light", 32, 16, 4), ("earth", 20, 20, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4)]
+          ("final", 20, 20, 2), ("final+bvh", 24, 24, 3), ("final_northstar", 48, 48, 4), ("simple_light", 32, 16, 4), ("earth", 20, 20, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4), ("two_spheres", 24, 24, 4)]
 
 
 def fname(kind, scene):
     return HERE / f"{kind}_{scene.replace('+', '_')}.npz"
 
 
-def main():
+def main(only=None):
     assert ro.available(), "build oracle/_ref/libref_oracle.so first (make -C oracle ref)"
     for name in TRACE:
+        if only and name not in only:
+            continue
         rs, rays = make_rays(name, n_primary=220, seed=21)
         np.savez_compressed(fname("trace", name), rays=rays, hits_a=rs.trace(rays, 0.001, FLT_MAX, seed=13),
                             hits_b=rs.trace(rays, 0.0, 400.0, seed=13), seed=13)
     for name, nx, ny, ns in RENDER:
+        if only and name not in only:
+            continue
         sums, st = ro.RefScene(name, tagged=True).render(nx, ny, ns, seed=4242, rng_mode=1)
         np.savez_compressed(fname("render", name), sums=sums, nx=nx, ny=ny, ns=ns, seed=4242, rays=st["rays"], aabb=st["aabb"])
+    if only:
+        return
     rng = np.random.default_rng(5)
     ro.RefScene("two_perlin", tagged=False)  # perlin tables of the never-seeded drand48 stream
     xyz = np.concatenate([rng.normal(scale=3, size=(400, 3)), rng.normal(scale=300, size=(400, 3))]).astype(np.float32)
@@ -64,4 +70,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(set(sys.argv[1:]) or None)  # optional scene names: regenerate only those trace/render fixtures

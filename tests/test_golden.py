@@ -141,3 +141,59 @@ def test_device_epilogue_reproduces_the_references_own_lines(rtnw, ctx):
         dev = torch.from_numpy(sums).cuda()
         assert np.array_equal(ctx.quantize_device(dev.data_ptr(), nx, ny, ns, clamp255=True), clamped), ns
         assert np.array_equal(ctx.quantize_device(dev.data_ptr(), nx, ny, ns, clamp255=False), raw), ns
+
+
+def _bilinear_numpy(img, u, v):
+    """numpy float32 restatement of the bilinear option (texel centres at i + 0.5, flipped u and v, edges clamped)"""
+    ny, nx, _ = img.shape
+    f = np.float32
+    fx = (f(1) - u) * f(nx) - f(0.5)
+    fy = (f(1) - v) * f(ny) - f(0.5)
+    x0, y0 = np.floor(fx), np.floor(fy)
+    wx, wy = (fx - x0)[:, None], (fy - y0)[:, None]
+    i0, i1 = np.clip(x0.astype(np.int64), 0, nx - 1), np.clip(x0.astype(np.int64) + 1, 0, nx - 1)
+    j0, j1 = np.clip(y0.astype(np.int64), 0, ny - 1), np.clip(y0.astype(np.int64) + 1, 0, ny - 1)
+    c = lambda j, i: img[j, i].astype(np.float32) / f(255.0)
+    top = (f(1) - wx) * c(j0, i0) + wx * c(j0, i1)
+    bot = (f(1) - wx) * c(j1, i0) + wx * c(j1, i1)
+    return (f(1) - wy) * top + wy * bot
+
+
+def _bilinear_case(rtnw):
+    import ctypes as C
+    hs = rtnw.HostScene("earth_bilinear")
+    d = hs.desc
+    tex = [i for i in range(d.n_textures) if d.textures[i].kind == 3][0]
+    t = d.textures[tex]
+    assert t.flags & rtnw.TEXF_BILINEAR
+    img = np.frombuffer(C.string_at(C.addressof(d.images.contents) + t.i0, 3 * t.i1 * t.i2), dtype=np.uint8).reshape(t.i2, t.i1, 3)
+    rng = np.random.default_rng(8)
+    uv = np.concatenate([rng.random((4000, 2)), [[0, 0], [1, 1], [0, 1], [1, 0], [0.5, 0.5]], rng.random((200, 2)) * 1e-3,
+                         1 - rng.random((200, 2)) * 1e-3]).astype(np.float32)
+    uvp = np.concatenate([uv, np.zeros((len(uv), 3), np.float32)], axis=1)
+    return hs, tex, img, uv, uvp
+
+
+def test_bilinear_image_texture_option_oracle(rtnw):
+    """image_texture's bilinear option (not in the reference): the C restatement against a numpy restatement,
+    and the nearest-texel default untouched by the flag's existence"""
+    hs, tex, img, uv, uvp = _bilinear_case(rtnw)
+    got = op.eval_texture(rtnw, hs.desc_ptr, tex, uvp)
+    assert np.allclose(got, _bilinear_numpy(img, uv[:, 0], uv[:, 1]), rtol=0, atol=2e-7)
+    near = rtnw.HostScene("earth")
+    tn = [i for i in range(near.desc.n_textures) if near.desc.textures[i].kind == 3][0]
+    assert near.desc.textures[tn].flags == 0
+    assert not np.allclose(op.eval_texture(rtnw, near.desc_ptr, tn, uvp), got, atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_bilinear_image_texture_option_gpu(rtnw, ctx):
+    hs, tex, img, uv, uvp = _bilinear_case(rtnw)
+    ds = ctx.upload(hs.desc_ptr)
+    got = ds.eval_texture(tex, uvp)
+    assert np.allclose(got, _bilinear_numpy(img, uv[:, 0], uv[:, 1]), rtol=0, atol=2e-7)
+    assert np.array_equal(got, op.eval_texture(rtnw, hs.desc_ptr, tex, uvp))
+    a, _ = ds.render(hs.camera(48, 48), hs.params(nx=48, ny=48, ns=4, seed=3))
+    b, _ = op.render(rtnw, hs.desc_ptr, hs.camera(48, 48), hs.params(nx=48, ny=48, ns=4, seed=3))
+    assert np.isclose(a, b, rtol=2e-5, atol=1e-6).all(axis=2).mean() > 0.99
+    ds.close()
