@@ -514,6 +514,12 @@ __device__ __forceinline__ void scan_run(const scene_view& S, int first, int nre
 #ifndef RTNW_PREFETCH
 #define RTNW_PREFETCH 0
 #endif
+#ifndef RTNW_PLAN1
+#define RTNW_PLAN1 1   // the round plan is computed by one thread (0: by every thread, the round-1 form)
+#endif
+#ifndef RTNW_SIGNLOAD
+#define RTNW_SIGNLOAD 1   // near / far planes of a node task loaded by the ray's signs (carried in the task word) instead of selected (0: round-1 form)
+#endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <int GROUP>
 __device__ __forceinline__ void group_sync() {
@@ -541,6 +547,7 @@ struct coop_smem {
     float4 acc[GROUP];    // k_render: the owner's work item — xyz = sum of its finished samples, w = next sample index k (int bits)
     int4 span[GROUP];     // k_render: the owner's work item — x = first sample of its pixel in this call (s_begin), y = end index of
                           // its range, z = pixel, w = range
+    int4 plan;            // RTNW_PLAN1: the round's plan (take, base, node_threads, drain), computed by thread 0 alone
     hkey_t key[GROUP];
     uint32_t q[QN + QL];  // [0, QN): node task stack; [QN, QN + QL): gate ring (one array: a push is a single predicated store)
     int n[3];             // node stack height, one buffer per round (read r % 3, popped/pushed (r + 1) % 3, cleared (r + 2) % 3)
@@ -558,11 +565,12 @@ struct coop_smem {
 #define RTNW_AGW 256     // private gate-task stack of a warp
 #define RTNW_ARING 1024  // shared ring (one for node tasks, one for gate tasks), a power of two
 #define RTNW_EMPTY 0xffffffffu
-// task = owner slot (9 bits) | wide node index or gate index (23 bits)
-#define RTNW_IDX_BITS 23
-#define RTNW_TASK(slot, idx) (((uint32_t)(slot) << RTNW_IDX_BITS) | (uint32_t)(idx))
-#define RTNW_TASK_SLOT(task) ((int)((task) >> RTNW_IDX_BITS))
+// task = owner slot (9 bits) | signs of the ray's direction (3 bits, RTNW_SIGNLOAD) | wide node index or gate index (20 bits)
+#define RTNW_IDX_BITS 20
+#define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 23) | (uint32_t)(idx))
+#define RTNW_TASK_SLOT(task) ((int)((task) >> 23))
 #define RTNW_TASK_IDX(task) ((task) & ((1u << RTNW_IDX_BITS) - 1u))
+#define RTNW_TASK_SIGNS(task) ((task) & (7u << RTNW_IDX_BITS))
 
 // once per kernel, before the first closest-hit query (followed by a group_sync)
 template <int GROUP>
@@ -605,7 +613,14 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
         int base = 0;
         if (lane == 0 && b) base = atomicAdd(&sm.n[r3], __popc(b));
         base = __shfl_sync(FULL, base, 0);
-        if (active) sm.q[base + __popc(b & lt_mask)] = RTNW_TASK(tid, root);
+        if (active) {
+            uint32_t t0 = RTNW_TASK(tid, root);
+#if RTNW_SIGNLOAD
+            const float4 ri = sm.ray_i[tid];  // written by this thread: which plane of a slab the ray meets first
+            t0 |= ((ri.x < 0.f ? 1u : 0u) | (ri.y < 0.f ? 2u : 0u) | (ri.z < 0.f ? 4u : 0u)) << RTNW_IDX_BITS;
+#endif
+            sm.q[base + __popc(b & lt_mask)] = t0;
+        }
     }
     group_sync<GROUP>();
 #pragma unroll 1
@@ -616,6 +631,24 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
         const int queued = (int)(ltail - lh);
         if (tid == 0) sm.n[prv] = 0;
         if (n == 0 && queued == 0) { r3 = nxt; break; }
+#if RTNW_PLAN1
+        // The round's plan is computed by ONE thread and read by the others after the barrier they wait at anyway: the
+        // ~50 instructions of it cost issue slots in one warp instead of all ten (they were 14 % of all instructions).
+        if (tid == 0) {
+            const int room_ = (QN - n - 3 * tree_depth) / 3;
+            const int take_ = (queued > QL - 4 * GROUP) ? 0 : min(min(n, GROUP), max(room_, 1));
+            const int nt_ = (take_ + 31) & ~31;
+            const int drain_ = min(queued, (GROUP - nt_) >> 1);
+            sm.plan = make_int4(take_, n - take_, nt_, drain_);
+            sm.n[nxt] = n - take_; sm.lh[nxt] = lh + (unsigned)drain_;  // pop both
+        }
+        group_sync<GROUP>();
+        const int4 pl = sm.plan;
+        const int take = pl.x, base = pl.y, node_threads = pl.z, drain = pl.w;
+        uint32_t task = 0;
+        if (tid < take) task = sm.q[base + tid];
+        else if (tid >= node_threads && tid - node_threads < 2 * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> 1)) & (QL - 1))];
+#else
         // node tasks this round: none while the gate ring is nearly full; otherwise as many as the stack has room for
         const int room = (QN - n - 3 * tree_depth) / 3;
         const int take = (queued > QL - 4 * GROUP) ? 0 : min(min(n, GROUP), max(room, 1));
@@ -626,6 +659,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
         if (tid < take) task = sm.q[base + tid];
         else if (tid >= node_threads && tid - node_threads < 2 * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> 1)) & (QL - 1))];
         if (tid == 0) { sm.n[nxt] = base; sm.lh[nxt] = lh + (unsigned)drain; }  // pop both
+#endif
 #ifdef RTNW_ROUND_STATS
         if (tid == 0) {
             RTNW_STAT(0, 1); RTNW_STAT(1, take); RTNW_STAT(2, drain); RTNW_STAT(8, n); RTNW_STAT(9, queued);
@@ -635,7 +669,9 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             stat_busy = busy; stat_c = clock64();
         }
 #endif
+#if !RTNW_PLAN1
         group_sync<GROUP>();
+#endif
         const int slot = RTNW_TASK_SLOT(task);
         if (tid < node_threads) {
             // ---- node warps: test the <= 4 child boxes of one wide node per lane, push what passed.  Straight-line code
@@ -643,7 +679,6 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             // without a task reads node 0 / slot 0 and masks its results.
             const bool live = tid < take;
             const float4* N = S.wnodes + 8 * (size_t)(live ? RTNW_TASK_IDX(task) : 0u);
-            const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
             const float4 rf = __ldg(N + 6);
             const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
             const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
@@ -652,10 +687,28 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             // the key only ever decreases) instead of the un-narrowed range the reference hands down
             const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[slot], ro.w)) : ro.w;
             bool pass[4];
+#if RTNW_SIGNLOAD
+            // aabb::hit's swap of (t0, t1) when invD < 0 (PSC/aabb.h:41-42) picks, per axis, which of the min / max planes is met
+            // first; the ray's three signs travel in the task word, so the near and far planes of the four boxes are simply
+            // LOADED from the right rows of the node instead of selected value by value (24 selects per task)
+            const unsigned sg = task >> RTNW_IDX_BITS;
+            const float4 nx4 = __ldg(N + ((sg & 1u) ? 3 : 0)), fx4 = __ldg(N + ((sg & 1u) ? 0 : 3));
+            const float4 ny4 = __ldg(N + ((sg & 2u) ? 4 : 1)), fy4 = __ldg(N + ((sg & 2u) ? 1 : 4));
+            const float4 nz4 = __ldg(N + ((sg & 4u) ? 5 : 2)), fz4 = __ldg(N + ((sg & 4u) ? 2 : 5));
+#define RTNW_SLAB(c) (!(fminf(fminf(fminf((fx4.c - o.x) * inv.x, t_hi), (fy4.c - o.y) * inv.y), (fz4.c - o.z) * inv.z) <= \
+                        fmaxf(fmaxf(fmaxf((nx4.c - o.x) * inv.x, t_min), (ny4.c - o.y) * inv.y), (nz4.c - o.z) * inv.z)) || (t_hi != t_hi))
+            pass[0] = live & (ref[0] != RTNW_REF_NONE) & RTNW_SLAB(x);
+            pass[1] = live & (ref[1] != RTNW_REF_NONE) & RTNW_SLAB(y);
+            pass[2] = live & (ref[2] != RTNW_REF_NONE) & RTNW_SLAB(z);
+            pass[3] = live & (ref[3] != RTNW_REF_NONE) & RTNW_SLAB(w);
+#undef RTNW_SLAB
+#else
+            const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
             pass[0] = live & (ref[0] != RTNW_REF_NONE) & hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, t_hi);
             pass[1] = live & (ref[1] != RTNW_REF_NONE) & hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, t_hi);
             pass[2] = live & (ref[2] != RTNW_REF_NONE) & hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, t_hi);
             pass[3] = live & (ref[3] != RTNW_REF_NONE) & hit_aabb6(mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, o, inv, t_min, t_hi);
+#endif
             if (COUNT && live) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
 #if RTNW_PREFETCH
             {   // the children that passed are popped a round (>= 1000 cycles) from now: pull their lines into L1 off the critical path
@@ -702,7 +755,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
                 const int at_n = base_n + __popc(bn[j] & lt_mask);
                 const int at_l = QN + (int)((base_l + (unsigned)__popc(bl[j] & lt_mask)) & (unsigned)(QL - 1));
                 const bool fits = isn ? at_n < QN : ring_ok;
-                if (pass[j] & fits) sm.q[isn ? at_n : at_l] = RTNW_TASK(slot, isn ? ref[j] : ~ref[j]);
+                if (pass[j] & fits) sm.q[isn ? at_n : at_l] = RTNW_TASK(slot, isn ? ref[j] : ~ref[j]) | RTNW_TASK_SIGNS(task);
                 ok &= !pass[j] | fits;
                 base_n += __popc(bn[j]); base_l += (unsigned)__popc(bl[j]);
             }
