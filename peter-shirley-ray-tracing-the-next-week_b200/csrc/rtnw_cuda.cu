@@ -64,8 +64,11 @@ __device__ __forceinline__ float from_fixed(unsigned long long u) {
     return (float)((double)(long long)u * (1.0 / 2199023255552.0));  // 2^-41, one rounding
 }
 
-typedef coop_smem<RTNW_GROUP> group_smem;
-struct block_smem { group_smem g[RTNW_BLOCK / RTNW_GROUP]; };
+typedef coop_smem<RTNW_GROUP, 1> group_smem;   // reference-exact kernels: one BVH item at a time
+typedef coop_smem<RTNW_GROUP, 2> group_smem2;  // RTNW_F_FAST_BVH kernels: two BVH items traversed together (two ray frames)
+template <bool FAST> struct smem_of { typedef group_smem type; };
+template <> struct smem_of<true> { typedef group_smem2 type; };
+template <bool FAST> struct block_smem { typename smem_of<FAST>::type g[RTNW_BLOCK / RTNW_GROUP]; };
 
 // The sample loop of PSC/main.cpp:299-313 as ONE persistent megakernel.
 //
@@ -82,7 +85,8 @@ struct block_smem { group_smem g[RTNW_BLOCK / RTNW_GROUP]; };
 template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const render_args P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    group_smem& sm = reinterpret_cast<block_smem*>(smem_raw)->g[threadIdx.x / RTNW_GROUP];
+    typedef typename smem_of<FAST>::type SM;
+    SM& sm = reinterpret_cast<block_smem<FAST>*>(smem_raw)->g[threadIdx.x / RTNW_GROUP];
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const int nx = P.p.nx, ny = P.p.ny;
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
     const bool denan = (P.p.flags & RTNW_F_DE_NAN) != 0;
     const bool sky = P.p.background == RTNW_BG_SKY;
 
-    coop_init<RTNW_GROUP>(sm);
+    coop_init<RTNW_GROUP, SM>(sm);
     group_sync<RTNW_GROUP>();
     int r3 = 0;  // index of the cooperative traversal's next round, mod 3 (coop_bvh_item)
 #ifdef RTNW_ROUND_STATS
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 #ifdef RTNW_ROUND_STATS
         const long long c0 = clock64();
 #endif
-        const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT, FAST>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt, r3);
+        const hkey_t key = coop_closest_hit<RTNW_GROUP, COUNT, FAST, SM>(P.S, sm, wr, tracing, P.p.t_min, P.p.t_max, mk, cnt, r3);
 #ifdef RTNW_ROUND_STATS
         if (threadIdx.x == 0) { RTNW_STAT(10, 1); RTNW_STAT(11, clock64() - c0); }
         const long long c1 = clock64();
@@ -261,7 +265,8 @@ template <bool FAST>
 __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const rtnw_ray* __restrict__ rays, size_t n, float t_min,
                                                       float t_max, uint64_t seed, rtnw_hit* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    group_smem& sm = reinterpret_cast<block_smem*>(smem_raw)->g[threadIdx.x / RTNW_GROUP];
+    typedef typename smem_of<FAST>::type SM;
+    SM& sm = reinterpret_cast<block_smem<FAST>*>(smem_raw)->g[threadIdx.x / RTNW_GROUP];
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = q < n;  // idle threads of the last block still work on the block's BVH tasks
     rtnw_ray in;
@@ -276,10 +281,10 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     mk.k0 = (uint32_t)seed; mk.k1 = (uint32_t)(seed >> 32); mk.pixel = in.key; mk.sample = 0; mk.depth = 0;
     trav_counters cnt;
     cnt.box_tests = 0; cnt.prim_tests = 0;
-    coop_init<RTNW_GROUP>(sm);
+    coop_init<RTNW_GROUP, SM>(sm);
     group_sync<RTNW_GROUP>();
     int r3 = 0;
-    const hkey_t key = coop_closest_hit<RTNW_GROUP, false, FAST>(S, sm, r, active, t_min, t_max, mk, cnt, r3);
+    const hkey_t key = coop_closest_hit<RTNW_GROUP, false, FAST, SM>(S, sm, r, active, t_min, t_max, mk, cnt, r3);
     if (!active) return;
     hit_t h;
     key_to_hit(S, key, t_max, h);
@@ -771,7 +776,7 @@ struct stream_builder {
         max_wide_depth = 0;
         root_out = emit_wide(bt, broot, 0);
         depth_out = max_wide_depth + 1;
-        if (RTNW_GROUP + 3 * depth_out + 8 > group_smem::QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
+        if (2 * RTNW_GROUP + 3 * depth_out + 8 > group_smem::QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
         return true;
     }
 
@@ -846,8 +851,8 @@ template <bool COUNT, bool FAST>
 int render_occupancy(rtnw_ctx* ctx, int* out) {
     int& bps = ctx->blocks_per_sm[(COUNT ? 1 : 0) + (FAST ? 2 : 0)];
     if (bps == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_render<COUNT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT, FAST>, RTNW_BLOCK, sizeof(block_smem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_render<COUNT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem<FAST>)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_render<COUNT, FAST>, RTNW_BLOCK, sizeof(block_smem<FAST>)));
         if (bps < 1) bps = 1;
     }
     *out = bps;
@@ -866,7 +871,7 @@ int launch_render(rtnw_ctx* ctx, const render_args& a, cudaStream_t st) {
 #ifdef RTNW_TUNING  // A/B builds only (scripts/ab_build.sh): the product library reads no environment on the launch path
     if (const char* e = getenv("RTNW_GRID_BLOCKS")) { const int v = atoi(e); if (v > 0) blocks = v; }
 #endif
-    k_render<COUNT, FAST><<<blocks, RTNW_BLOCK, sizeof(block_smem), st>>>(a);
+    k_render<COUNT, FAST><<<blocks, RTNW_BLOCK, sizeof(block_smem<FAST>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RTNW_OK;
 }
@@ -1381,11 +1386,11 @@ int rtnw_trace(rtnw_ctx* ctx, const rtnw_scene* scene, const rtnw_ray* rays, siz
     CUDA_TRY(cudaMemcpyAsync(d_rays.p, rays, n * sizeof(rtnw_ray), cudaMemcpyHostToDevice, ctx->stream));
     const unsigned grid = (unsigned)((n + RTNW_BLOCK - 1) / RTNW_BLOCK);
     if (flags & RTNW_F_FAST_BVH) {
-        CUDA_TRY(cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
-        k_trace<true><<<grid, RTNW_BLOCK, sizeof(block_smem), ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
+        CUDA_TRY(cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem<true>)));
+        k_trace<true><<<grid, RTNW_BLOCK, sizeof(block_smem<true>), ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem)));
-        k_trace<false><<<grid, RTNW_BLOCK, sizeof(block_smem), ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
+        CUDA_TRY(cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(block_smem<false>)));
+        k_trace<false><<<grid, RTNW_BLOCK, sizeof(block_smem<false>), ctx->stream>>>(scene->view, d_rays.as<rtnw_ray>(), n, t_min, t_max, seed, d_out.as<rtnw_hit>());
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n * sizeof(rtnw_hit), cudaMemcpyDeviceToHost, ctx->stream));

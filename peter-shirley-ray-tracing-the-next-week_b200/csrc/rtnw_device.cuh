@@ -534,15 +534,18 @@ __device__ __forceinline__ void group_sync() {
 #ifndef RTNW_QL_ABS
 #define RTNW_QL_ABS 4096  // gate ring size (a power of two; 0: RTNW_QL_MULT * GROUP, for power-of-two block sizes)
 #endif
-template <int GROUP>
+template <int GROUP, int FRAMES = 1>
 struct coop_smem {
-    static_assert(GROUP <= 512 && GROUP % 32 == 0, "a task carries its owner slot in 9 bits");
+    static_assert(GROUP <= 512 && GROUP % 32 == 0 && FRAMES * GROUP <= 1024, "a task carries its (frame, owner) slot in 10 bits");
     static constexpr int QN = RTNW_QN_MULT * GROUP;   // node task stack
     static constexpr int QL = RTNW_QL_ABS ? RTNW_QL_ABS : RTNW_QL_MULT * GROUP;   // gate queue (circular, power of two); node work pauses while < 4*GROUP slots are free
+    static constexpr int NFRAMES = FRAMES;
     static_assert((QL & (QL - 1)) == 0, "the gate ring must be a power of two");
-    float4 ray_o[GROUP];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
-    float4 ray_d[GROUP];  // d.xyz, w = dot(d,d)
-    float4 ray_i[GROUP];  // 1/d, w = time
+    // the ray of owner `tid` in the frame of a BVH item lives at index frame * GROUP + tid ("virtual slot"; FRAMES = 2 only in
+    // the RTNW_F_FAST_BVH kernels, which traverse two BVH items at once)
+    float4 ray_o[FRAMES * GROUP];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
+    float4 ray_d[FRAMES * GROUP];  // d.xyz, w = dot(d,d)
+    float4 ray_i[FRAMES * GROUP];  // 1/d, w = time
     uint4 mkey[GROUP];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
     float4 acc[GROUP];    // k_render: the owner's work item — xyz = sum of its finished samples, w = next sample index k (int bits)
     int4 span[GROUP];     // k_render: the owner's work item — x = first sample of its pixel in this call (s_begin), y = end index of
@@ -565,21 +568,22 @@ struct coop_smem {
 #define RTNW_AGW 256     // private gate-task stack of a warp
 #define RTNW_ARING 1024  // shared ring (one for node tasks, one for gate tasks), a power of two
 #define RTNW_EMPTY 0xffffffffu
-// task = owner slot (9 bits) | signs of the ray's direction (3 bits, RTNW_SIGNLOAD) | wide node index or gate index (20 bits)
-#define RTNW_IDX_BITS 20
-#define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 23) | (uint32_t)(idx))
-#define RTNW_TASK_SLOT(task) ((int)((task) >> 23))
+// task = virtual slot (frame * GROUP + owner, 10 bits) | signs of the ray's direction in that frame (3 bits) | wide node
+// index or gate index (19 bits)
+#define RTNW_IDX_BITS 19
+#define RTNW_TASK(slot, idx) (((uint32_t)(slot) << 22) | (uint32_t)(idx))
+#define RTNW_TASK_SLOT(task) ((int)((task) >> 22))
 #define RTNW_TASK_IDX(task) ((task) & ((1u << RTNW_IDX_BITS) - 1u))
 #define RTNW_TASK_SIGNS(task) ((task) & (7u << RTNW_IDX_BITS))
 
 // once per kernel, before the first closest-hit query (followed by a group_sync)
-template <int GROUP>
-__device__ __forceinline__ void coop_init(coop_smem<GROUP>& sm) {
+template <int GROUP, class SM>
+__device__ __forceinline__ void coop_init(SM& sm) {
     const int tid = threadIdx.x % GROUP;
     if (tid < 3) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
     if (tid == 3) { sm.lt = 0u; sm.overflow = 0; }
 #if RTNW_ASYNC
-    static_assert((GROUP / 32) * (RTNW_ANW + RTNW_AGW) + 2 * RTNW_ARING <= coop_smem<GROUP>::QN + coop_smem<GROUP>::QL, "async queues do not fit q[]");
+    static_assert((GROUP / 32) * (RTNW_ANW + RTNW_AGW) + 2 * RTNW_ARING <= SM::QN + SM::QL, "async queues do not fit q[]");
     if (tid < 2) { sm.ring_head[tid] = 0u; sm.ring_tail[tid] = 0u; sm.idle[tid] = 0; }
     for (int i = tid; i < 2 * RTNW_ARING; i += GROUP) sm.q[(GROUP / 32) * (RTNW_ANW + RTNW_AGW) + i] = RTNW_EMPTY;
 #endif
@@ -592,11 +596,11 @@ __device__ __forceinline__ void coop_init(coop_smem<GROUP>& sm) {
 // lane from the top of the stack; the remaining warps take one queued gate per lane (leaf->hit for its leaves), so
 // thin node rounds are filled with leaf work instead of idling at the barrier; when the stack is empty all warps
 // drain the gate queue.
-template <int GROUP, bool COUNT, bool FAST>
-__device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GROUP>& sm, int root, int tree_depth, bool active,
+template <int GROUP, bool COUNT, bool FAST, class SM>
+__device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int nf, int root0, int root1, int tree_depth, bool active,
                                               float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt, int& r3) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int QN = coop_smem<GROUP>::QN, QL = coop_smem<GROUP>::QL;
+    constexpr int QN = SM::QN, QL = SM::QL;
     const int tid = threadIdx.x % GROUP;  // index within the cooperating group
     const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
 #ifdef RTNW_ROUND_STATS
@@ -608,18 +612,21 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
     // the next item's root tasks then go to n[r3 + 1], cleared one round earlier, so entering an item needs no reset and no
     // barrier of its own: a thread still reading n[r3] / lh[r3] / lt of the final round never sees them change.
     if (tid == 0) sm.lh[r3] = sm.lt;  // empty ring; lh[r3] was last read three rounds ago
-    {   // one task per ray: the root of the gate tree
+    {   // one task per ray and frame: the root of the gate tree of each of the nf (1 or 2) items traversed together
         const unsigned b = __ballot_sync(FULL, active);
         int base = 0;
-        if (lane == 0 && b) base = atomicAdd(&sm.n[r3], __popc(b));
+        if (lane == 0 && b) base = atomicAdd(&sm.n[r3], __popc(b) * nf);
         base = __shfl_sync(FULL, base, 0);
         if (active) {
-            uint32_t t0 = RTNW_TASK(tid, root);
-#if RTNW_SIGNLOAD
-            const float4 ri = sm.ray_i[tid];  // written by this thread: which plane of a slab the ray meets first
-            t0 |= ((ri.x < 0.f ? 1u : 0u) | (ri.y < 0.f ? 2u : 0u) | (ri.z < 0.f ? 4u : 0u)) << RTNW_IDX_BITS;
-#endif
-            sm.q[base + __popc(b & lt_mask)] = t0;
+#pragma unroll
+            for (int f = 0; f < SM::NFRAMES; ++f) {
+                if (f < nf) {
+                    const int v = f * GROUP + tid;
+                    const float4 ri = sm.ray_i[v];  // written by this thread: which plane of a slab the ray meets first
+                    const uint32_t sg = (ri.x < 0.f ? 1u : 0u) | (ri.y < 0.f ? 2u : 0u) | (ri.z < 0.f ? 4u : 0u);
+                    sm.q[base + __popc(b & lt_mask) * nf + f] = RTNW_TASK(v, f ? root1 : root0) | (sg << RTNW_IDX_BITS);
+                }
+            }
         }
     }
     group_sync<GROUP>();
@@ -672,7 +679,8 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
 #if !RTNW_PLAN1
         group_sync<GROUP>();
 #endif
-        const int slot = RTNW_TASK_SLOT(task);
+        const int slot = RTNW_TASK_SLOT(task);  // virtual slot: the ray in its item's frame
+        const int own = (SM::NFRAMES > 1 && slot >= GROUP) ? slot - GROUP : slot;  // the thread that owns the ray (key, medium key)
         if (tid < node_threads) {
             // ---- node warps: test the <= 4 child boxes of one wide node per lane, push what passed.  Straight-line code
             // (no short-circuit): the four slab tests are independent and interleave; a lane of the last node warp
@@ -685,7 +693,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             const int ref[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
             // RTNW_F_FAST_BVH: boxes are tested against the ray's closest hit SO FAR (any value read is a valid upper bound:
             // the key only ever decreases) instead of the un-narrowed range the reference hands down
-            const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[slot], ro.w)) : ro.w;
+            const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[own], ro.w)) : ro.w;
             bool pass[4];
 #if RTNW_SIGNLOAD
             // aabb::hit's swap of (t0, t1) when invD < 0 (PSC/aabb.h:41-42) picks, per axis, which of the min / max planes is met
@@ -769,13 +777,13 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, coop_smem<GRO
             if (leaf >= 0) {
                 const float4 A0 = __ldg(&S.recs[leaf].a), B0 = __ldg(&S.recs[leaf].b);
                 const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
-                const uint4 mq = sm.mkey[slot];
+                const uint4 mq = sm.mkey[own];
                 ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
                 medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-                const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[slot], ro.w)) : ro.w;
+                const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[own], ro.w)) : ro.w;
                 k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, t_hi, mk, cnt);
             }
-            if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
+            if (k != RTNW_KEY_NONE) atomicMin(&sm.key[own], k);
         }
         group_sync<GROUP>();
         r3 = nxt;
@@ -802,8 +810,8 @@ __device__ __forceinline__ unsigned ld_vol(const unsigned* p) { return *reinterp
 __device__ __forceinline__ int ld_vol(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 // take up to `want` tasks from ring `which` into dst[0..got); warp-uniform result
-template <int GROUP>
-__device__ __forceinline__ int ring_steal(coop_smem<GROUP>& sm, uint32_t* ring, int which, int want, uint32_t* dst, unsigned lane) {
+template <int GROUP, class SM>
+__device__ __forceinline__ int ring_steal(SM& sm, uint32_t* ring, int which, int want, uint32_t* dst, unsigned lane) {
     constexpr unsigned FULL = 0xffffffffu;
     int got = 0;
     unsigned h = 0;
@@ -829,8 +837,8 @@ __device__ __forceinline__ int ring_steal(coop_smem<GROUP>& sm, uint32_t* ring, 
     return got;
 }
 // give src[0..k) (k <= 32) to ring `which` if it has room; warp-uniform result
-template <int GROUP>
-__device__ __forceinline__ bool ring_donate(coop_smem<GROUP>& sm, uint32_t* ring, int which, int k, const uint32_t* src, unsigned lane) {
+template <int GROUP, class SM>
+__device__ __forceinline__ bool ring_donate(SM& sm, uint32_t* ring, int which, int k, const uint32_t* src, unsigned lane) {
     constexpr unsigned FULL = 0xffffffffu;
     int ok = 0;
     unsigned t = 0;
@@ -854,8 +862,8 @@ __device__ __forceinline__ bool ring_donate(coop_smem<GROUP>& sm, uint32_t* ring
     return true;
 }
 
-template <int GROUP, bool COUNT>
-__device__ __forceinline__ void async_bvh_item(const scene_view& S, coop_smem<GROUP>& sm, int root, int tree_depth, bool active,
+template <int GROUP, bool COUNT, class SM>
+__device__ __forceinline__ void async_bvh_item(const scene_view& S, SM& sm, int root, int tree_depth, bool active,
                                                float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt, int& phase) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int NWARP = GROUP / 32, NW = RTNW_ANW, GW = RTNW_AGW;
@@ -895,8 +903,8 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, coop_smem<GR
                 __threadfence_block();
                 idle = false;
             }
-            nN = ring_steal<GROUP>(sm, ringN, 0, 32, myN, lane);
-            if (nN == 0) nG = ring_steal<GROUP>(sm, ringG, 1, 16, myG, lane);
+            nN = ring_steal<GROUP, SM>(sm, ringN, 0, 32, myN, lane);
+            if (nN == 0) nG = ring_steal<GROUP, SM>(sm, ringG, 1, 16, myG, lane);
             if (nN == 0 && nG == 0) {
                 idle = true;
                 if (lane == 0) atomicAdd(&sm.idle[ph], 1);
@@ -911,7 +919,7 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, coop_smem<GR
             const int room = (NW - nN - 3 * tree_depth) / 3;
             int take = min(min(nN, 32), min(max(room, 1), (GW - nG) >> 2));
             if (take == nN && take < 32 && room >= 32) {  // top the batch up (ring_steal returns 0 at once when the ring is empty)
-                const int got = ring_steal<GROUP>(sm, ringN, 0, 32 - take, myN + nN, lane);
+                const int got = ring_steal<GROUP, SM>(sm, ringN, 0, 32 - take, myN + nN, lane);
                 if (got) __threadfence_block();
                 nN += got; take += got;
             }
@@ -952,7 +960,7 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, coop_smem<GR
             // ---- gate batch: leaf->hit(r, tmin, tmax0) for the one or two leaves of 16 gates, one lane per leaf
             int take = min(nG, 16);
             if (take == nG && take < 16) {
-                const int got = ring_steal<GROUP>(sm, ringG, 1, 16 - take, myG + nG, lane);
+                const int got = ring_steal<GROUP, SM>(sm, ringG, 1, 16 - take, myG + nG, lane);
                 if (got) __threadfence_block();
                 nG += got; take += got;
             }
@@ -979,10 +987,10 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, coop_smem<GR
         // ---- share: more than two batches of one kind -> one batch goes to the ring (if it has room)
 #ifndef RTNW_ASYNC_NODONATE
         if (nN >= 64) {
-            if (ring_donate<GROUP>(sm, ringN, 0, 32, myN + nN - 32, lane)) { nN -= 32; RTNW_STAT(5, 1); }
+            if (ring_donate<GROUP, SM>(sm, ringN, 0, 32, myN + nN - 32, lane)) { nN -= 32; RTNW_STAT(5, 1); }
         }
         if (nG >= 48) {
-            if (ring_donate<GROUP>(sm, ringG, 1, 16, myG + nG - 16, lane)) { nG -= 16; RTNW_STAT(6, 1); }
+            if (ring_donate<GROUP, SM>(sm, ringG, 1, 16, myG + nG - 16, lane)) { nG -= 16; RTNW_STAT(6, 1); }
         }
 #endif
     }
@@ -992,55 +1000,107 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, coop_smem<GR
 
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
 // thread without a ray passes active = false and still works on the other threads' BVH tasks.
-template <int GROUP, bool COUNT, bool FAST>
-__device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, coop_smem<GROUP>& sm, const ray_t& wr, bool active,
+// One element of the top-level list that is a plain list of primitives: scanned by each owner in lockstep.
+template <bool COUNT>
+__device__ __forceinline__ void scan_list_item(const scene_view& S, int i, int next, const ray_t& r, float a, float t_min, float best_t,
+                                               const medium_key& mk, hkey_t& key, trav_counters& cnt) {
+    float lim = best_t;
+#pragma unroll 1
+    for (int j = i + 1; j < next;) {
+        const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
+        const uint32_t rk = __float_as_uint(B.z) & 15u;
+        if (rk >= K_RUN_SPHERE) {  // a run header (uniform over the block): the specialised loop takes the next A.x records
+            const int nrec = __float_as_int(A.x);
+            if (rk == K_RUN_SPHERE) scan_run<COUNT, K_RUN_SPHERE>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
+            else if (rk == K_RUN_SPHERELIKE) scan_run<COUNT, K_RUN_SPHERELIKE>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
+            else scan_run<COUNT, K_RUN_BOX>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
+            j += 1 + nrec;
+            continue;
+        }
+        bool hit; float t; int face;
+        const int step = test_record<COUNT>(S, j, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
+        if (hit) { lim = t; key = make_key(t, j, face); }  // list narrowing: an accepted hit is the new closest
+        j += step;
+    }
+}
+
+template <int GROUP, bool COUNT, bool FAST, class SM>
+__device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, SM& sm, const ray_t& wr, bool active,
                                                    float t_min, float t_max, const medium_key& mk, trav_counters& cnt, int& r3) {
     const int tid = threadIdx.x % GROUP;
     sm.key[tid] = RTNW_KEY_NONE;
     sm.mkey[tid] = make_uint4(mk.pixel, mk.sample, mk.depth, 0u);
-    int i = 0;
-    for (;;) {  // the elements of the top-level hitable_list, in order (PSC/hitable_list.h:24-30); uniform over the block
-        const float4 IA = __ldg(&S.recs[i].a), IB = __ldg(&S.recs[i].b);
-        const uint32_t tag = __float_as_uint(IB.z);
-        if ((tag & 15u) != K_ITEM) break;  // K_END
-        const int next = __float_as_int(IA.x);
-        hkey_t key = sm.key[tid];
-        const float best_t = key_t_or(key, t_max);  // closest_so_far: the t_max this element receives
-        ray_t r = wr;
-        xform_ray(S.xforms, tag >> 8, r);
-        const float a = dot(r.d, r.d);
-        if (__float_as_int(IB.w) == RTNW_ITEM_BVH) {
-            sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
-            sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
-            sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
+    if (!FAST) {
+        int i = 0;
+        for (;;) {  // the elements of the top-level hitable_list, in order (PSC/hitable_list.h:24-30); uniform over the block
+            const float4 IA = __ldg(&S.recs[i].a), IB = __ldg(&S.recs[i].b);
+            const uint32_t tag = __float_as_uint(IB.z);
+            if ((tag & 15u) != K_ITEM) break;  // K_END
+            const int next = __float_as_int(IA.x);
+            hkey_t key = sm.key[tid];
+            const float best_t = key_t_or(key, t_max);  // closest_so_far: the t_max this element receives
+            ray_t r = wr;
+            xform_ray(S.xforms, tag >> 8, r);
+            const float a = dot(r.d, r.d);
+            if (__float_as_int(IB.w) == RTNW_ITEM_BVH) {
+                sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
+                sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
+                sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
 #if RTNW_ASYNC
-            __syncwarp();
-            async_bvh_item<GROUP, COUNT>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
+                __syncwarp();
+                async_bvh_item<GROUP, COUNT, SM>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
 #else
-            coop_bvh_item<GROUP, COUNT, FAST>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
+                coop_bvh_item<GROUP, COUNT, false, SM>(S, sm, 1, __float_as_int(IA.y), 0, __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
 #endif
-        } else if (active) {
-            float lim = best_t;
-#pragma unroll 1
-            for (int j = i + 1; j < next;) {
-                const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
-                const uint32_t rk = __float_as_uint(B.z) & 15u;
-                if (rk >= K_RUN_SPHERE) {  // a run header (uniform over the block): the specialised loop takes the next A.x records
-                    const int nrec = __float_as_int(A.x);
-                    if (rk == K_RUN_SPHERE) scan_run<COUNT, K_RUN_SPHERE>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
-                    else if (rk == K_RUN_SPHERELIKE) scan_run<COUNT, K_RUN_SPHERELIKE>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
-                    else scan_run<COUNT, K_RUN_BOX>(S, j + 1, nrec, r, a, t_min, lim, key, cnt);
-                    j += 1 + nrec;
-                    continue;
-                }
-                bool hit; float t; int face;
-                const int step = test_record<COUNT>(S, j, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
-                if (hit) { lim = t; key = make_key(t, j, face); }  // list narrowing: an accepted hit is the new closest
-                j += step;
+            } else if (active) {
+                scan_list_item<COUNT>(S, i, next, r, a, t_min, best_t, mk, key, cnt);
+                sm.key[tid] = key;
             }
-            sm.key[tid] = key;
+            i = next;
         }
-        i = next;
+    } else {
+        // RTNW_F_FAST_BVH.  The closest hit does not depend on the order in which the elements of the list are examined
+        // (except among candidates of equal t), only the reference's TEST SET does: an element is handed the closest hit of
+        // the elements before it as its t_max.  The fast mode gives that up: first every plain element (narrowing as usual),
+        // then the BVH elements TWO AT A TIME in one cooperative traversal, each ray present once per item frame — half the
+        // rounds of the latency chain for a scene with two BVHs — and boxes / leaves tested against the running closest hit.
+        for (int i = 0;;) {
+            const float4 IA = __ldg(&S.recs[i].a), IB = __ldg(&S.recs[i].b);
+            const uint32_t tag = __float_as_uint(IB.z);
+            if ((tag & 15u) != K_ITEM) break;
+            const int next = __float_as_int(IA.x);
+            if (__float_as_int(IB.w) != RTNW_ITEM_BVH && active) {
+                hkey_t key = sm.key[tid];
+                ray_t r = wr;
+                xform_ray(S.xforms, tag >> 8, r);
+                scan_list_item<COUNT>(S, i, next, r, dot(r.d, r.d), t_min, key_t_or(key, t_max), mk, key, cnt);
+                sm.key[tid] = key;
+            }
+            i = next;
+        }
+        int nf = 0, root0 = 0, root1 = 0, depth = 0;
+        for (int i = 0;;) {
+            const float4 IA = __ldg(&S.recs[i].a), IB = __ldg(&S.recs[i].b);
+            const uint32_t tag = __float_as_uint(IB.z);
+            const bool end = (tag & 15u) != K_ITEM;
+            if (!end && __float_as_int(IB.w) == RTNW_ITEM_BVH) {
+                ray_t r = wr;
+                xform_ray(S.xforms, tag >> 8, r);
+                const int v = nf * GROUP + tid;
+                sm.ray_o[v] = make_float4(r.o.x, r.o.y, r.o.z, key_t_or(sm.key[tid], t_max));
+                sm.ray_d[v] = make_float4(r.d.x, r.d.y, r.d.z, dot(r.d, r.d));
+                sm.ray_i[v] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
+                if (nf == 0) root0 = __float_as_int(IA.y); else root1 = __float_as_int(IA.y);
+                depth = max(depth, __float_as_int(IA.z));
+                ++nf;
+            }
+            if (nf == SM::NFRAMES || (end && nf > 0)) {
+                coop_bvh_item<GROUP, COUNT, true, SM>(S, sm, nf, root0, root1, depth, active, t_min, mk.k0, mk.k1, cnt, r3);
+                nf = 0; depth = 0;
+            }
+            if (end) break;
+            i = __float_as_int(IA.x);
+        }
     }
     group_sync<GROUP>();  // nobody may overwrite sm.key before every owner has read its result
     const hkey_t out = sm.key[tid];
