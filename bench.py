@@ -373,7 +373,7 @@ def main():
         # algorithmic HBM bytes of one launch: the scene image read once + the frame written once (+ the fixed-point plane of the
         # sample-range sums written and read back once when a pixel's samples are cut into ranges)
         hbm_bytes = image_bytes + nx * ny * 3 * 4 + (2 * nx * ny * 3 * 8 if sample_ranges > 1 else 0)
-        traffic, traffic_note = measured_traffic(args.config, world)
+        traffic, traffic_note = measured_traffic(args.config, world) if not (args.flags & 4) else (None, "no capture of the fast-mode kernel")
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

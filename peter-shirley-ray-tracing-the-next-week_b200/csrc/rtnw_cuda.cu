@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 #endif
     // The work item of a thread (pixel, sample range, running sum) lives in shared memory: it is touched when a path
     // ends, i.e. once every few rounds, and would otherwise occupy eight registers across every round.
-    const int me = threadIdx.x % RTNW_GROUP;
+    int me = threadIdx.x % RTNW_GROUP;  // index of this thread's work item in sm.acc / sm.span (RTNW_MIGRATE: travels with the ray)
     bool alive = true, need = true, has_item = false;
     int depth = 0;
     f3 T = mk3(0.f, 0.f, 0.f);
@@ -192,6 +192,65 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
         if (threadIdx.x == 0) { RTNW_STAT(10, 1); RTNW_STAT(11, clock64() - c0); }
         const long long c1 = clock64();
 #endif
+#if RTNW_MIGRATE
+        // ---- rays change threads so that a warp shades rays of ONE kind: the next step of a ray (miss / light: the path ends
+        // and a new one starts; lambertian; metal; dielectric; isotropic) is known from its hit.  Each ray's state (20 words)
+        // is written to shared memory at its rank in a counting sort by that class and read back by the thread of that rank;
+        // the work item stays where it is (sm.acc / sm.span[me], `me` travels with the ray).  What a ray computes does not
+        // depend on the thread that runs it, so results are unchanged.
+        bool tracing_ = tracing;
+        hkey_t key_ = key;
+        {
+            static_assert(RTNW_GROUP == RTNW_BLOCK, "ray migration uses block barriers");
+            int cls = 0;
+            if (tracing) {
+                cls = 1;
+                if (key != RTNW_KEY_NONE) {
+                    const int mat_id = __float_as_int(__ldg(&P.S.recs[key_rec(key)].b).w);
+                    const float4 m0 = __ldg(reinterpret_cast<const float4*>(P.S.materials + mat_id));
+                    const uint32_t mkind = __float_as_uint(m0.x);
+                    cls = mkind == RTNW_MAT_DIFFUSE_LIGHT ? 2 : mkind == RTNW_MAT_METAL ? 5 : mkind == RTNW_MAT_DIELECTRIC ? 6 : mkind == RTNW_MAT_ISOTROPIC ? 7 : 3;
+                    if (cls == 3 && __float_as_uint(__ldg(reinterpret_cast<const float4*>(P.S.textures + __float_as_int(m0.y))).x) != RTNW_TEX_CONSTANT) cls = 4;
+                }
+            }
+            const unsigned same = __match_any_sync(FULL, cls);
+            const int leader = __ffs(same) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(&sm.bins[cls], __popc(same));
+            base = __shfl_sync(FULL, base, leader);
+            const int off = base + __popc(same & ((1u << lane) - 1u));
+            __syncthreads();
+            const int4 b0 = *reinterpret_cast<const int4*>(&sm.bins[0]), b1 = *reinterpret_cast<const int4*>(&sm.bins[4]);
+            const int cnt8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            int pos = off;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) pos += c < cls ? cnt8[c] : 0;
+            float4* xch = reinterpret_cast<float4*>(sm.q);  // both queues are empty between closest-hit queries
+            const unsigned flags = (alive ? 1u : 0u) | (need ? 2u : 0u) | (has_item ? 4u : 0u) | (tracing ? 8u : 0u);
+            xch[5 * pos + 0] = make_float4(wr.o.x, wr.o.y, wr.o.z, wr.time);
+            xch[5 * pos + 1] = make_float4(wr.d.x, wr.d.y, wr.d.z, T.x);
+            xch[5 * pos + 2] = make_float4(T.y, T.z, __uint_as_float((uint32_t)g.x), __uint_as_float((uint32_t)(g.x >> 32)));
+            xch[5 * pos + 3] = make_float4(__uint_as_float(g.sample), __int_as_float(depth), __uint_as_float(flags), __int_as_float(me));
+            xch[5 * pos + 4] = make_float4(__uint_as_float((uint32_t)key), __uint_as_float((uint32_t)(key >> 32)), 0.f, 0.f);
+            __syncthreads();
+            if (threadIdx.x < 8) sm.bins[threadIdx.x] = 0;
+            const float4 x0 = xch[5 * threadIdx.x + 0], x1 = xch[5 * threadIdx.x + 1], x2 = xch[5 * threadIdx.x + 2],
+                         x3 = xch[5 * threadIdx.x + 3], x4 = xch[5 * threadIdx.x + 4];
+            wr.o = mk3(x0.x, x0.y, x0.z); wr.time = x0.w;
+            wr.d = mk3(x1.x, x1.y, x1.z);
+            T = mk3(x1.w, x2.x, x2.y);
+            g.x = (unsigned long long)__float_as_uint(x2.z) | ((unsigned long long)__float_as_uint(x2.w) << 32);
+            g.sample = __float_as_uint(x3.x);
+            depth = __float_as_int(x3.y);
+            const unsigned fl = __float_as_uint(x3.z);
+            alive = fl & 1u; need = (fl & 2u) != 0; has_item = (fl & 4u) != 0; tracing_ = (fl & 8u) != 0;
+            me = __float_as_int(x3.w);
+            key_ = (hkey_t)__float_as_uint(x4.x) | ((hkey_t)__float_as_uint(x4.y) << 32);
+            __syncthreads();  // the queues are used again by the next closest-hit query
+        }
+#define tracing tracing_
+#define key key_
+#endif
         // ---- one level of color(), PSC/main.cpp:25-46, in iterative form
         if (tracing) {
             ++n_rays;
@@ -237,6 +296,10 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                 sm.acc[me] = acc;
             }
         }
+#if RTNW_MIGRATE
+#undef tracing
+#undef key
+#endif
 #ifdef RTNW_ROUND_STATS
         if (threadIdx.x == 0) RTNW_STAT(13, clock64() - c1);
 #endif

@@ -517,6 +517,9 @@ __device__ __forceinline__ void scan_run(const scene_view& S, int first, int nre
 #ifndef RTNW_PLAN1
 #define RTNW_PLAN1 1   // the round plan is computed by one thread (0: by every thread, the round-1 form)
 #endif
+#ifndef RTNW_MIGRATE
+#define RTNW_MIGRATE 0
+#endif
 #ifndef RTNW_SIGNLOAD
 #define RTNW_SIGNLOAD 1   // near / far planes of a node task loaded by the ray's signs (carried in the task word) instead of selected (0: round-1 form)
 #endif
@@ -550,6 +553,7 @@ struct coop_smem {
     float4 acc[GROUP];    // k_render: the owner's work item — xyz = sum of its finished samples, w = next sample index k (int bits)
     int4 span[GROUP];     // k_render: the owner's work item — x = first sample of its pixel in this call (s_begin), y = end index of
                           // its range, z = pixel, w = range
+    int bins[8];          // RTNW_MIGRATE: rays per shading class of the current round (zero between rounds)
     int4 plan;            // RTNW_PLAN1: the round's plan (take, base, node_threads, drain), computed by thread 0 alone
     hkey_t key[GROUP];
     uint32_t q[QN + QL];  // [0, QN): node task stack; [QN, QN + QL): gate ring (one array: a push is a single predicated store)
@@ -582,6 +586,7 @@ __device__ __forceinline__ void coop_init(SM& sm) {
     const int tid = threadIdx.x % GROUP;
     if (tid < 3) { sm.n[tid] = 0; sm.lh[tid] = 0u; }
     if (tid == 3) { sm.lt = 0u; sm.overflow = 0; }
+    if (tid >= 8 && tid < 16) sm.bins[tid - 8] = 0;
 #if RTNW_ASYNC
     static_assert((GROUP / 32) * (RTNW_ANW + RTNW_AGW) + 2 * RTNW_ARING <= SM::QN + SM::QL, "async queues do not fit q[]");
     if (tid < 2) { sm.ring_head[tid] = 0u; sm.ring_tail[tid] = 0u; sm.idle[tid] = 0; }
