@@ -113,7 +113,13 @@ enum rtnw_texture_kind {
     RTNW_TEX_CONSTANT = 0, /* PSC/texture.h:16-28   c = color */
     RTNW_TEX_CHECKER = 1,  /* PSC/texture.h:30-45   i0 = even texture, i1 = odd texture */
     RTNW_TEX_NOISE = 2,    /* PSC/texture.h:47-59   c[0] = scale */
-    RTNW_TEX_IMAGE = 3     /* PSC/surface_texture.h i0 = byte offset into the image pool, i1 = nx, i2 = ny (RGB8) */
+    RTNW_TEX_IMAGE = 3,    /* PSC/surface_texture.h i0 = byte offset into the image pool, i1 = nx, i2 = ny (RGB8) */
+    /* The three intermediate noise textures of the reference's Chapter 4 (README.md:516-630; the sources of the shipped
+     * "Chapter04_Perlin noise_noise*.ppm"): value = (1,1,1) * noise(p) over a table of 256 FLOATS, which a scene using them
+     * passes in perlin_ranvec[3*i] (the x components; README.md:536-542 `ranfloat`): */
+    RTNW_TEX_NOISE_HASH = 4,      /* README.md:516-524   ranfloat[perm_x[int(4x)&255] ^ perm_y[..] ^ perm_z[..]]           */
+    RTNW_TEX_NOISE_TRILINEAR = 5, /* README.md:599-611   trilinear interpolation of the eight lattice values (PSC/perlin.h:11-23) */
+    RTNW_TEX_NOISE_HERMITE = 6    /* README.md:619-630   the same with Hermite-smoothed u, v, w                               */
 };
 /* rtnw_texture.flags of an image texture: sample the four texels around (u, v) and blend them (texel centres at i + 0.5, edges
  * clamped) instead of the reference's nearest-texel lookup (PSC/surface_texture.h:19-30).  Not in the reference: an option. */

@@ -28,7 +28,8 @@ const char* rtnw_host_last_error(void);
 /* Build a named scene with the process-global drand48 stream reset to its never-seeded state, the perlin tables
  * drawn first (1533 draws, as the reference's static initialisers do, PSC/perlin.h:108-111), then the builder.
  * Names: "ch01_random", "two_perlin", "cornell_box", "cornell_smoke", "final", "final_northstar",
- * "simple_light", "two_spheres", "earth", "random_scene", "test", "stress_shells" and "twin_bvh" (test fixtures, not reference scenes); suffix "+bvh" wraps the flat top-level list in one
+ * "simple_light", "two_spheres", "earth", "random_scene", "test", "perlin_v1" / "perlin_v2" / "perlin_v3" (the Chapter 4 noise
+ * drafts of README.md:516-630), "stress_shells" and "twin_bvh" (test fixtures, not reference scenes); suffix "+bvh" wraps the flat top-level list in one
  * bvh_node(list, n, 0, 1) (PSC/bvh.h:97-121), e.g. "final+bvh"; suffix ":ch01" / ":ch03" / ":ch07" / ":ch08" selects the camera and
  * integrator settings of that chapter snapshot's main() (t_min 0.0 / 0.01, aperture 0.1, its image size, no de_nan), e.g.
  * "cornell_smoke:ch08" is TNW/Chapter08_Volume.cpp as shipped. */

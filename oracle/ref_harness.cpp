@@ -247,6 +247,60 @@ hitable* h_two_perlin() {
     return new hitable_list(list, 2);
 }
 
+// The three intermediate noise functions of README.md Chapter 4, before perlin.h reached its shipped form (the sources of
+// TNW/Chapter04_Perlin noise_noise{1,2 smoth,3 hermite cubic smoth}.ppm; SURVEY.md §4: "source not shipped").  Restated from the
+// README excerpts: variant 1 = hash only (README.md:516-524), 2 = trilinear interpolation of the lattice values (README.md:599-611,
+// i.e. the reference's own trilinear_interp, PSC/perlin.h:11-23), 3 = the same with Hermite-smoothed u,v,w (README.md:619-630).
+// They index a table of 256 FLOATS (ranfloat[i] = drand48(), README.md:536-542), drawn before the three permutations.
+// The texture is the book's at that stage: value = (1,1,1) * noise(p).
+float* g_ranfloat = NULL;
+struct readme_noise_texture : public texture {
+    int variant;
+    explicit readme_noise_texture(int v) : variant(v) {}
+    float noise(const vec3& p) const {
+        if (variant == 1) {
+            int i = int(4 * p.x()) & 255;
+            int j = int(4 * p.y()) & 255;
+            int k = int(4 * p.z()) & 255;
+            return g_ranfloat[perlin::perm_x[i] ^ perlin::perm_y[j] ^ perlin::perm_z[k]];
+        }
+        float u = p.x() - floor(p.x());
+        float v = p.y() - floor(p.y());
+        float w = p.z() - floor(p.z());
+        if (variant == 3) {
+            u = u * u * (3 - 2 * u);
+            v = v * v * (3 - 2 * v);
+            w = w * w * (3 - 2 * w);
+        }
+        int i = floor(p.x());
+        int j = floor(p.y());
+        int k = floor(p.z());
+        float c[2][2][2];
+        for (int di = 0; di < 2; di++)
+            for (int dj = 0; dj < 2; dj++)
+                for (int dk = 0; dk < 2; dk++)
+                    c[di][dj][dk] = g_ranfloat[perlin::perm_x[(i + di) & 255] ^ perlin::perm_y[(j + dj) & 255] ^ perlin::perm_z[(k + dk) & 255]];
+        return trilinear_interp(c, u, v, w);
+    }
+    virtual vec3 value(float u, float v, const vec3& p) const { return vec3(1, 1, 1) * noise(p); }
+};
+
+void regenerate_readme_tables() {  // README.md:536-570: ranfloat, then perm_x, perm_y, perm_z
+    g_ranfloat = new float[256];
+    for (int i = 0; i < 256; i++) g_ranfloat[i] = ref_hook_drand48();
+    perlin::perm_x = perlin_generate_perm();
+    perlin::perm_y = perlin_generate_perm();
+    perlin::perm_z = perlin_generate_perm();
+}
+
+hitable* h_perlin_variant(int variant) {  // two_perlin_spheres() of that stage (README.md:588-596): both spheres carry the noise
+    texture* pertext = new readme_noise_texture(variant);
+    hitable** list = new hitable*[2];
+    list[0] = new sphere(vec3(0, -1000, 0), 1000, new lambertian(pertext));
+    list[1] = new sphere(vec3(0, 2, 0), 2, new lambertian(pertext));
+    return new hitable_list(list, 2);
+}
+
 unsigned char* h_synthetic_earth(int& nx, int& ny) {  // same integer pattern as the host library's stand-in image
     nx = 1024;
     ny = 512;
@@ -374,6 +428,7 @@ ref_scene* ref_scene_build(const char* name_c, int tagged_build) {
     quiet_cout quiet;
     G.mode = 0;
     srand48(0x1234ABCD);  // glibc's never-seeded state
+    if (name.compare(0, 8, "perlin_v") == 0) regenerate_readme_tables(); else
     regenerate_perlin_tables();
     ref_scene_impl* S = new ref_scene_impl();
     S->tagged_build = tagged_build != 0;
@@ -390,6 +445,7 @@ ref_scene* ref_scene_build(const char* name_c, int tagged_build) {
     else if (name == "random_scene") w = random_scene();
     else if (name == "test") w = test();
     else if (name == "final_northstar") { w = h_final_northstar(*S); pre_tagged = true; }
+    else if (name == "perlin_v1" || name == "perlin_v2" || name == "perlin_v3") w = h_perlin_variant(name[8] - '0');
     else { delete S; return NULL; }
     hitable_list* flat = static_cast<hitable_list*>(w);
     if (!pre_tagged)
@@ -464,6 +520,10 @@ int ref_scene_dump(const ref_scene* S, float* out, int max_leaves) {
         }
     }
     return n;
+}
+
+void ref_ranfloat_table(float* out256) {
+    for (int i = 0; i < 256; ++i) out256[i] = g_ranfloat ? g_ranfloat[i] : 0.f;
 }
 
 void ref_perlin_tables(float* ranvec768, int* px, int* py, int* pz) {
@@ -599,6 +659,7 @@ void ref_eval_texture(int which, const float* c, const float* uvp, size_t n, flo
     if (which == 0) t = new constant_texture(vec3(c[0], c[1], c[2]));
     else if (which == 1) t = new checker_texture(new constant_texture(vec3(c[0], c[1], c[2])), new constant_texture(vec3(c[3], c[4], c[5])));
     else if (which == 2) t = new noise_texture(c[0]);
+    else if (which >= 4 && which <= 6) t = new readme_noise_texture(which - 3);  // needs the tables of a perlin_v* scene build
     else { int nx, ny; unsigned char* d = h_synthetic_earth(nx, ny); t = new image_texture(d, nx, ny); }
     for (size_t i = 0; i < n; ++i) {
         const float* q = uvp + 5 * i;

@@ -404,6 +404,36 @@ static float perlin_turb(const rtnw_scene_desc* d, vec3 p) {
     }
     return fabsf(accum);
 }
+/* README.md:516-630: the Chapter 4 noise functions before perlin.h's shipped form; ranfloat[i] = perlin_ranvec[3*i] */
+static float readme_noise(const rtnw_scene_desc* d, uint32_t kind, vec3 p) {
+    const float* rf = d->perlin_ranvec;
+    if (kind == RTNW_TEX_NOISE_HASH) {
+        int i = (int)(4 * p.e[0]) & 255;
+        int j = (int)(4 * p.e[1]) & 255;
+        int k = (int)(4 * p.e[2]) & 255;
+        return rf[3 * (d->perlin_perm_x[i] ^ d->perlin_perm_y[j] ^ d->perlin_perm_z[k])];
+    }
+    float u = p.e[0] - floorf(p.e[0]);
+    float v = p.e[1] - floorf(p.e[1]);
+    float w = p.e[2] - floorf(p.e[2]);
+    if (kind == RTNW_TEX_NOISE_HERMITE) {
+        u = u * u * (3 - 2 * u);
+        v = v * v * (3 - 2 * v);
+        w = w * w * (3 - 2 * w);
+    }
+    int i = floorf(p.e[0]);
+    int j = floorf(p.e[1]);
+    int k = floorf(p.e[2]);
+    float accum = 0;
+    for (int di = 0; di < 2; di++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int dk = 0; dk < 2; dk++) {
+                const float c = rf[3 * (d->perlin_perm_x[(i + di) & 255] ^ d->perlin_perm_y[(j + dj) & 255] ^ d->perlin_perm_z[(k + dk) & 255])];
+                accum += (di * u + (1 - di) * (1 - u)) * (dj * v + (1 - dj) * (1 - v)) * (dk * w + (1 - dk) * (1 - w)) * c;
+            }
+    return accum;
+}
+
 static vec3 texture_value(const rtnw_scene_desc* d, int tex, float u, float v, vec3 p) {
     const rtnw_texture* t = &d->textures[tex];
     switch (t->kind) {
@@ -412,6 +442,12 @@ static vec3 texture_value(const rtnw_scene_desc* d, int tex, float u, float v, v
             float sines = sinf(10 * p.e[0]) * sinf(10 * p.e[1]) * sinf(10 * p.e[2]);
             if (sines < 0) return texture_value(d, t->i1 /* odd */, u, v, p);
             return texture_value(d, t->i0 /* even */, u, v, p);
+        }
+        case RTNW_TEX_NOISE_HASH:
+        case RTNW_TEX_NOISE_TRILINEAR:
+        case RTNW_TEX_NOISE_HERMITE: {
+            const float n = readme_noise(d, t->kind, p);
+            return smul(n, V(1, 1, 1));
         }
         case RTNW_TEX_NOISE: {
             const float scale = t->c[0];

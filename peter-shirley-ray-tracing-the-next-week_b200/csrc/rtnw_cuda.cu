@@ -863,7 +863,7 @@ struct stream_builder {
                 if (x.i0 < 0 || x.i1 <= 0 || x.i2 <= 0 || !d.images ||
                     (uint64_t)x.i0 + 3ull * (uint64_t)x.i1 * (uint64_t)x.i2 > d.image_bytes)
                     return bad("image texture outside the image pool");
-            } else if (x.kind != RTNW_TEX_CONSTANT && x.kind != RTNW_TEX_NOISE) {
+            } else if (x.kind != RTNW_TEX_CONSTANT && x.kind != RTNW_TEX_NOISE && !(x.kind >= RTNW_TEX_NOISE_HASH && x.kind <= RTNW_TEX_NOISE_HERMITE)) {
                 return bad("unknown texture kind");
             }
         }

@@ -1226,6 +1226,35 @@ __device__ __forceinline__ float perlin_turb(const scene_view& S, f3 p) {
     return fabsf(accum);
 }
 
+// README.md:516-630: the Chapter 4 noise functions that preceded perlin.h's shipped form (RTNW_TEX_NOISE_HASH / _TRILINEAR /
+// _HERMITE); `ranfloat[i]` is S.ranvec[i].x.  Operation order as in the reference's trilinear_interp (PSC/perlin.h:11-23).
+__device__ __forceinline__ float readme_noise(const scene_view& S, uint32_t kind, f3 p) {
+    if (kind == RTNW_TEX_NOISE_HASH) {
+        const int i = (int)(4.f * p.x) & 255, j = (int)(4.f * p.y) & 255, k = (int)(4.f * p.z) & 255;
+        return __ldg(&S.ranvec[__ldg(&S.perm[i]) ^ __ldg(&S.perm[256 + j]) ^ __ldg(&S.perm[512 + k])]).x;
+    }
+    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    if (kind == RTNW_TEX_NOISE_HERMITE) {
+        u = u * u * (3.f - 2.f * u);
+        v = v * v * (3.f - 2.f * v);
+        w = w * w * (3.f - 2.f * w);
+    }
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    float accum = 0.f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const float c = __ldg(&S.ranvec[__ldg(&S.perm[(i + di) & 255]) ^ __ldg(&S.perm[256 + ((j + dj) & 255)]) ^ __ldg(&S.perm[512 + ((k + dk) & 255)])]).x;
+                accum += ((float)di * u + (float)(1 - di) * (1.f - u)) * ((float)dj * v + (float)(1 - dj) * (1.f - v)) *
+                         ((float)dk * w + (float)(1 - dk) * (1.f - w)) * c;
+            }
+    return accum;
+}
+
 // texture::value(u, v, p): PSC/texture.h:22-56, PSC/surface_texture.h:19-30
 __device__ __forceinline__ f3 texture_value(const scene_view& S, int tex, float u, float v, f3 p) {
     for (;;) {
@@ -1237,6 +1266,10 @@ __device__ __forceinline__ f3 texture_value(const scene_view& S, int tex, float 
             const float sines = sinf(10.f * p.x) * sinf(10.f * p.y) * sinf(10.f * p.z);
             tex = sines < 0.f ? __float_as_int(t0.z) /* odd */ : __float_as_int(t0.y) /* even */;
             continue;
+        }
+        if (kind >= RTNW_TEX_NOISE_HASH) {
+            const float n = readme_noise(S, kind, p);
+            return mk3(n, n, n);  // vec3(1,1,1) * noise(p)
         }
         if (kind == RTNW_TEX_NOISE) {
             const float scale = t1.x;

@@ -48,6 +48,7 @@ int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
     }
     // never-seeded drand48 state (glibc: X0 = 0x1234ABCD330E), then the tables the reference draws before main()
     srand48(0x1234ABCD);
+    if (name.compare(0, 8, "perlin_v") == 0) perlin::regenerate_readme(); else
     perlin::regenerate();
 
     using namespace rtnw_scenes;
@@ -82,6 +83,17 @@ int rtnw_host_scene_build(const char* name_c, rtnw_host_scene** out) {
     else if (name == "random_scene") { world = random_scene(); v = view_ch01(); v.emit = true; }
     else if (name == "test") { world = test_scene(); v = view_two_perlin(); v.sky = false; v.emit = true; }
     else if (name == "stress_shells") { world = stress_shells(); v = view_ch01(); v.aperture = 0.0f; }
+    else if (name == "perlin_v1" || name == "perlin_v2" || name == "perlin_v3") {
+        // two_perlin_spheres() of the reference's Chapter 4 drafts (README.md:588-596) with the noise function of that stage, and
+        // the main() settings of that time (the Ch03 snapshot's: aperture 0.1, t_min 0.0, sky, 200x100x100)
+        texture* pertext = new readme_noise_texture(name[8] - '0');
+        hitable** l = new hitable*[2];
+        l[0] = new sphere(vec3(0, -1000, 0), 1000, new lambertian(pertext));
+        l[1] = new sphere(vec3(0, 2, 0), 2, new lambertian(pertext));
+        world = new hitable_list(l, 2);
+        v = view_ch01();
+        v.t_min = 0.0f;
+    }
     else if (name == "twin_bvh") { world = twin_bvh(); v = view_ch01(); v.aperture = 0.0f; }
     else return fail(RTNW_ERR_INVALID, "unknown scene name: " + name);
     if (wrap) world = wrap_in_bvh(world, 0, 1);

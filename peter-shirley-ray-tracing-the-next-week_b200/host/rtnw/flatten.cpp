@@ -129,6 +129,13 @@ private:
                 rec.c[0] = static_cast<const noise_texture*>(t)->scale;
                 uses_noise_ = true;
                 break;
+            case tex_kind::readme_noise: {
+                const int variant = static_cast<const readme_noise_texture*>(t)->variant;
+                if (variant < 1 || variant > 3) throw unsupported("readme_noise_texture variant must be 1, 2 or 3");
+                rec.kind = RTNW_TEX_NOISE_HASH + (variant - 1);
+                uses_noise_ = true;
+                break;
+            }
             case tex_kind::image: {
                 const image_texture* im = static_cast<const image_texture*>(t);
                 if (!im->data || im->nx <= 0 || im->ny <= 0) throw unsupported("image_texture without pixels");

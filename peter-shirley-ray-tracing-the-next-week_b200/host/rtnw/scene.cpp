@@ -74,6 +74,15 @@ void perlin::regenerate() {
     perm_z = shuffled_identity();
 }
 
+void perlin::regenerate_readme() {
+    vec3* rv = new vec3[256];
+    for (int i = 0; i < 256; ++i) rv[i] = vec3(float(drand48()), 0, 0);  // float* p = new float[256]; p[i] = drand48()
+    ranvec = rv;
+    perm_x = shuffled_identity();
+    perm_y = shuffled_identity();
+    perm_z = shuffled_identity();
+}
+
 // ---- rotate_y, PSC/hitable.h:98-126 -----------------------------------------------------------------------------
 rotate_y::rotate_y(hitable* p, float angle) : ptr(p) {
     const float radians = (M_PI / 180.) * angle;

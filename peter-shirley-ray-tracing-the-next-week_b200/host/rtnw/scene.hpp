@@ -100,7 +100,7 @@ inline aabb surrounding_box(aabb b0, aabb b1) {
 
 // ------------------------------------------------------------------------------------------------ appearance
 namespace rtnw {
-enum class tex_kind { constant, checker, noise, image, user };
+enum class tex_kind { constant, checker, noise, image, readme_noise, user };
 enum class mat_kind { lambertian, metal, dielectric, diffuse_light, isotropic, user };
 enum class geo_kind { sphere, moving_sphere, rect_xy, rect_xz, rect_yz, box, flip, translate, rotate_y, list, bvh, medium, user };
 }  // namespace rtnw
@@ -140,6 +140,17 @@ public:
     static int* perm_y;
     static int* perm_z;
     static void regenerate();  // 768 + 3*255 draws
+    // the tables of the reference's Chapter 4 drafts (README.md:536-570): 256 floats `ranfloat` (kept in ranvec[i].x), then the
+    // three permutations — 256 + 3*255 draws
+    static void regenerate_readme();
+};
+// The three intermediate noise textures of README.md:516-630 (hash only / trilinear / Hermite-smoothed trilinear), value =
+// (1,1,1) * noise(p): regression scenes for the shipped Chapter04 images.  Needs perlin::regenerate_readme() tables.
+class readme_noise_texture : public texture {
+public:
+    int variant;  // 1, 2, 3
+    explicit readme_noise_texture(int v) : variant(v) {}
+    rtnw::tex_kind rtnw_kind() const override { return rtnw::tex_kind::readme_noise; }
 };
 class noise_texture : public texture {  // PSC/texture.h:47-59
 public:

@@ -21,7 +21,8 @@ from raysets import FLT_MAX, make_rays  # noqa: E402
 TRACE = ["ch01_random", "two_perlin", "cornell_box", "cornell_smoke", "final", "final+bvh", "final_northstar", "earth",
          "simple_light", "cornell_smoke+bvh", "random_scene+bvh", "test", "two_spheres"]
 RENDER = [("ch01_random", 32, 16, 4), ("two_perlin", 32, 16, 4), ("cornell_box", 24, 24, 6), ("cornell_smoke", 24, 24, 6),
-          ("final", 20, 20, 2), ("final+bvh", 24, 24, 3), ("final_northstar", 48, 48, 4), ("simple_light", 32, 16, 4), ("earth", 20, 20, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4), ("two_spheres", 24, 24, 4)]
+          ("final", 20, 20, 2), ("final+bvh", 24, 24, 3), ("final_northstar", 48, 48, 4), ("simple_light", 32, 16, 4), ("earth", 20, 20, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4), ("two_spheres", 24, 24, 4),
+          ("perlin_v1", 32, 16, 4), ("perlin_v2", 32, 16, 4), ("perlin_v3", 32, 16, 4)]
 
 
 def fname(kind, scene):
@@ -41,6 +42,14 @@ def main(only=None):
             continue
         sums, st = ro.RefScene(name, tagged=True).render(nx, ny, ns, seed=4242, rng_mode=1)
         np.savez_compressed(fname("render", name), sums=sums, nx=nx, ny=ny, ns=ns, seed=4242, rays=st["rays"], aabb=st["aabb"])
+    if not only or only & {"perlin_v1", "perlin_v2", "perlin_v3", "readme_units"}:
+        # the Chapter 4 noise drafts (README.md:516-630, restated in the harness): texture values at fixed points
+        rng = np.random.default_rng(6)
+        ro.RefScene("perlin_v1", tagged=False)  # their tables: ranfloat + permutations of the never-seeded stream
+        xyz = np.concatenate([rng.normal(scale=3, size=(600, 3)), rng.normal(scale=300, size=(300, 3)), rng.integers(-4, 5, (100, 3))]).astype(np.float32)
+        uvp = np.concatenate([np.zeros((len(xyz), 2), np.float32), xyz], axis=1)
+        np.savez_compressed(HERE / "units_readme_noise.npz", uvp=uvp, v1=ro.eval_texture(4, [], uvp), v2=ro.eval_texture(5, [], uvp),
+                            v3=ro.eval_texture(6, [], uvp))
     if only:
         return
     rng = np.random.default_rng(5)

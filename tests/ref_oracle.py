@@ -68,6 +68,9 @@ VIEWS = {
     "random_scene": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vfov=20, aperture=0.1, t_min=0.001, sky=1, emit=1, denan=0),
     "test": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vfov=20, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=0),
     "final": dict(lookfrom=(228, 278, -800), lookat=(278, 278, 0), vfov=40, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=1),
+    "perlin_v1": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vfov=20, aperture=0.1, t_min=0.0, sky=1, emit=0, denan=0),
+    "perlin_v2": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vfov=20, aperture=0.1, t_min=0.0, sky=1, emit=0, denan=0),
+    "perlin_v3": dict(lookfrom=(13, 2, 3), lookat=(0, 0, 0), vfov=20, aperture=0.1, t_min=0.0, sky=1, emit=0, denan=0),
     "final_northstar": dict(lookfrom=(228, 278, -800), lookat=(278, 278, 0), vfov=40, aperture=0.0, t_min=0.001, sky=0, emit=1, denan=1),
 }
 

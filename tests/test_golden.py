@@ -197,3 +197,30 @@ def test_bilinear_image_texture_option_gpu(rtnw, ctx):
     b, _ = op.render(rtnw, hs.desc_ptr, hs.camera(48, 48), hs.params(nx=48, ny=48, ns=4, seed=3))
     assert np.isclose(a, b, rtol=2e-5, atol=1e-6).all(axis=2).mean() > 0.99
     ds.close()
+
+
+def _readme_noise_textures(rtnw):
+    """{1,2,3} -> (HostScene, texture index) of the Chapter 4 noise drafts (README.md:516-630)"""
+    out = {}
+    for v in (1, 2, 3):
+        hs = rtnw.HostScene(f"perlin_v{v}")
+        tex = [i for i in range(hs.desc.n_textures) if hs.desc.textures[i].kind == 3 + v]
+        assert len(tex) == 1
+        out[v] = (hs, tex[0])
+    return out
+
+
+def test_oracle_port_reproduces_readme_noise_units(rtnw):
+    g = np.load(GOLD / "units_readme_noise.npz")
+    for v, (hs, tex) in _readme_noise_textures(rtnw).items():
+        assert np.array_equal(op.eval_texture(rtnw, hs.desc_ptr, tex, g["uvp"]), g[f"v{v}"]), v
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_readme_noise_units(rtnw, ctx):
+    """the Chapter 4 noise drafts on the GPU: bit for bit against the harness-side restatement's values"""
+    g = np.load(GOLD / "units_readme_noise.npz")
+    for v, (hs, tex) in _readme_noise_textures(rtnw).items():
+        ds = ctx.upload(hs.desc_ptr)
+        assert np.array_equal(ds.eval_texture(tex, g["uvp"]), g[f"v{v}"]), v
+        ds.close()

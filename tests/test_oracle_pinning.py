@@ -25,7 +25,9 @@ def test_port_closest_hit_bit_exact(rtnw, name):
 
 @pytest.mark.parametrize("name,nx,ny,ns", [("ch01_random", 48, 24, 4), ("two_perlin", 48, 24, 4), ("cornell_box", 32, 32, 6),
                                             ("cornell_smoke", 32, 32, 6), ("final", 24, 24, 2), ("final+bvh", 32, 32, 3),
-                                            ("final_northstar", 32, 32, 3), ("simple_light", 32, 16, 4), ("earth", 24, 24, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4)])
+                                            ("final_northstar", 32, 32, 3), ("simple_light", 32, 16, 4), ("earth", 24, 24, 3), ("random_scene", 40, 20, 4), ("test", 32, 16, 4), ("two_spheres", 24, 24, 4),
+                                            ("perlin_v1", 40, 20, 4), ("perlin_v2", 40, 20, 4), ("perlin_v3", 40, 20, 4),
+                                            ("cornell_smoke:ch08", 24, 24, 4), ("random_scene:ch03", 40, 20, 4)])
 def test_port_render_bit_exact(rtnw, name, nx, ny, ns):
     hs = rtnw.HostScene(name)
     got, st = op.render(rtnw, hs.desc_ptr, hs.camera(nx, ny), hs.params(nx=nx, ny=ny, ns=ns, seed=99))

@@ -3,7 +3,8 @@ TNW/Chapter03_Soild Texture.ppm, TNW/Chapter07_Instance_add box ratate and trans
 (tests/golden/shipped_ppm_means.json, written by tests/golden/make_ppm_means.py from the files themselves) must be
 reproduced to < 1 % by rendering the same builder with that snapshot's own main() settings: image size, 100 spp, t_min
 0.0 / 0.01, aperture 0.1, no de_nan, NO clamp to 255 (TNW/Chapter08_Volume.cpp:26,244-253) — scene names
-"random_scene:ch03", "cornell_box:ch07", "cornell_smoke:ch08".  The shipped files cannot be reproduced bit for bit (Apple
+"random_scene:ch03", "cornell_box:ch07", "cornell_smoke:ch08" — and, for the three Chapter04_Perlin noise_*.ppm,
+the README's intermediate noise functions (README.md:516-630; "perlin_v1/2/3"), whose sources the reference does not ship.  The shipped files cannot be reproduced bit for bit (Apple
 clang / libm, rand() jitter in Ch03); their means can."""
 import json
 from pathlib import Path
@@ -12,7 +13,9 @@ import numpy as np
 import pytest
 
 GOLD = Path(__file__).resolve().parent / "golden"
-CASES = [("random_scene:ch03", "Chapter03_Soild Texture.ppm"),
+CASES = [("perlin_v1", "Chapter04_Perlin noise_noise1.ppm"), ("perlin_v2", "Chapter04_Perlin noise_noise2 smoth.ppm"),
+         ("perlin_v3", "Chapter04_Perlin noise_noise3 hermite cubic smoth.ppm"),
+         ("random_scene:ch03", "Chapter03_Soild Texture.ppm"),
          ("cornell_box:ch07", "Chapter07_Instance_add box ratate and translate.ppm"),
          ("cornell_smoke:ch08", "Chapter08_Volume.ppm")]
 TOL = 0.01
@@ -46,10 +49,21 @@ def test_gpu_reproduces_shipped_ppm_mean_rgb(rtnw, ctx, name, ppm):
     _check(name, ppm, sums, 100, rtnw)
 
 
+@pytest.mark.parametrize("name,ppm", CASES[:3])
+def test_oracle_reproduces_shipped_chapter04_noise_mean_rgb(rtnw, name, ppm):
+    """CPU: the README's noise drafts through the C restatement (bit-identical to the harness restatement built on the
+    reference's own classes, tests/test_oracle_pinning.py) reproduce the shipped Chapter 4 images' means"""
+    import oracle_port as op
+    nx, ny, _ = _want(ppm)
+    hs = rtnw.HostScene(name)
+    sums, _ = op.render(rtnw, hs.desc_ptr, hs.camera(nx, ny), hs.params(seed=8))
+    _check(name, ppm, sums, 100, rtnw)
+
+
 def test_oracle_reproduces_shipped_ch08_mean_rgb(rtnw):
     """CPU: the same gate through the C restatement of the reference (pins the snapshot view and the fixture without a GPU)"""
     import oracle_port as op
-    name, ppm = CASES[2]
+    name, ppm = CASES[-1]
     nx, ny, _ = _want(ppm)
     hs = rtnw.HostScene(name)
     assert abs(hs.view.t_min - 0.01) < 1e-9
