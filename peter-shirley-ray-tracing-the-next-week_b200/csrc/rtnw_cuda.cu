@@ -621,6 +621,7 @@ struct stream_builder {
         bool cont = first_cont;
         size_t last_head = (size_t)-1;  // the record a leaf scan tests last (a moving sphere / medium head, not its trailing records)
         int32_t run_end = first;        // slots below this one already belong to a run that has its header
+        int32_t pad_spheres_until = first;  // plain spheres below this slot sit in a mixed sphere / moving-sphere run: padded to two records
         for (int32_t s = first; s < first + count; ++s) {
             if (allow_runs && s >= run_end) {  // does a run of plain spheres / (moving) spheres / boxes start here?
                 const int c0 = run_class(s, first + count);
@@ -634,8 +635,10 @@ struct stream_builder {
                         pure = pure && c == 1;
                         ++prims; nrec += c == 2 ? 2 : 1; q += c == 2 ? 2 : 1;
                     }
+                    pad_spheres_until = first;
                     if (prims >= MIN_RUN) {
                         const uint32_t k = sph ? (pure ? K_RUN_SPHERE : K_RUN_SPHERELIKE) : K_RUN_BOX;
+                        if (k == K_RUN_SPHERELIKE) { nrec = 2 * prims; pad_spheres_until = q; }  // every primitive of a mixed run takes two records
                         push(make_float4(bits(nrec), 0, 0, 0), 0, 0, RTNW_TAG(k, 0, 1, 0), 0, -1);
                     }
                     run_end = q;  // (short runs are not examined again)
@@ -651,7 +654,10 @@ struct stream_builder {
             if (!boundary && (p.mat < 0 || p.mat >= d.n_materials)) return bad("material index out of range");
             switch (kind) {
                 case RTNW_PRIM_SPHERE:
-                    push(make_float4(p.f[0], p.f[1], p.f[2], p.f[3]), 0, 0, RTNW_TAG(K_SPHERE, flip, cont, chain), p.mat, id);
+                    // in a mixed run a plain sphere is laid out like a moving one that does not move: shutter (0, 1), c1 = c0, so
+                    // that center(time) = c0 + time * (c0 - c0) = c0 exactly and the run's loop needs no case distinction
+                    push(make_float4(p.f[0], p.f[1], p.f[2], p.f[3]), 0, s < pad_spheres_until ? 1.f : 0.f, RTNW_TAG(K_SPHERE, flip, cont, chain), p.mat, id);
+                    if (s < pad_spheres_until) push(make_float4(p.f[0], p.f[1], p.f[2], 0), 0, 0, RTNW_TAG(K_EXT, 0, 1, 0), -1, id);
                     break;
                 case RTNW_PRIM_MOVING_SPHERE: {
                     if (s + 1 >= first + count || RTNW_KX_KIND(d.prims[s + 1].kx) != RTNW_PRIM_EXT)

@@ -450,29 +450,81 @@ __device__ __forceinline__ void scan_run(const scene_view& S, int first, int nre
                                          hkey_t& key, trav_counters& cnt) {
     const int end = first + nrec;
     if (RUN == K_RUN_SPHERE) {  // PSC/sphere.h:25-52, one record each
-#pragma unroll 4
-        for (int j = first; j < end; ++j) {
+        // four spheres per step: the discriminants (the part every sphere pays) are four independent straight-line chains that
+        // interleave; the roots and the narrowing, which only a sphere the ray's line meets needs, follow in record order
+        int j = first;
+#pragma unroll 1
+        for (; j + 4 <= end; j += 4) {
+            float bq[4], dq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 A = __ldg(&S.recs[j + q].a);
+                const f3 oc = r.o - mk3(A.x, A.y, A.z);
+                bq[q] = dot(oc, r.d);
+                const float cc = dot(oc, oc) - A.w * A.w;
+                dq[q] = bq[q] * bq[q] - a * cc;
+            }
+            if ((dq[0] > 0.f) | (dq[1] > 0.f) | (dq[2] > 0.f) | (dq[3] > 0.f)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (dq[q] > 0.f) {
+                        const float sq = sqrtf(dq[q]);
+                        float temp = (-bq[q] - sq) / a;
+                        if (temp < lim && temp > t_min) { lim = temp; key = make_key(temp, j + q, 0); }
+                        else {
+                            temp = (-bq[q] + sq) / a;
+                            if (temp < lim && temp > t_min) { lim = temp; key = make_key(temp, j + q, 0); }
+                        }
+                    }
+                }
+            }
+        }
+        for (; j < end; ++j) {
             const float4 A = __ldg(&S.recs[j].a);
             float t;
             if (hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
         }
         if (COUNT) cnt.prim_tests += nrec;
-    } else if (RUN == K_RUN_SPHERELIKE) {  // spheres and moving spheres mixed (PSC/sphere.h:92-118: two records); the kind test is warp-uniform
+    } else if (RUN == K_RUN_SPHERELIKE) {
+        // spheres and moving spheres mixed (PSC/sphere.h:92-118).  Every primitive of such a run takes TWO records (the
+        // upload pads a plain sphere with a continuation record), so record positions do not depend on kinds and four
+        // primitives' centres and discriminants are computed as independent straight-line chains; a plain sphere is stored
+        // as a moving sphere that does not move (shutter (0, 1), c1 = c0: its centre at any time is c0 exactly).
+        int j = first;
 #pragma unroll 1
-        for (int j = first; j < end;) {
-            const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
-            f3 c = mk3(A.x, A.y, A.z);
-            int step = 1;
-            if ((__float_as_uint(B.z) & 15u) == K_MSPHERE) {
-                const float4 A2 = __ldg(&S.recs[j + 1].a);
-                c = moving_center(c, mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
-                step = 2;
+        for (; j + 8 <= end; j += 8) {
+            float bq[4], dq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 A = __ldg(&S.recs[j + 2 * q].a), B = __ldg(&S.recs[j + 2 * q].b), A2 = __ldg(&S.recs[j + 2 * q + 1].a);
+                const f3 oc = r.o - moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);  // a plain sphere: c0 + time * 0
+                bq[q] = dot(oc, r.d);
+                const float cc = dot(oc, oc) - A.w * A.w;
+                dq[q] = bq[q] * bq[q] - a * cc;
             }
-            if (COUNT) cnt.prim_tests++;
-            float t;
-            if (hit_sphere(c, A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
-            j += step;
+            if ((dq[0] > 0.f) | (dq[1] > 0.f) | (dq[2] > 0.f) | (dq[3] > 0.f)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (dq[q] > 0.f) {
+                        const float sq = sqrtf(dq[q]);
+                        float temp = (-bq[q] - sq) / a;
+                        if (temp < lim && temp > t_min) { lim = temp; key = make_key(temp, j + 2 * q, 0); }
+                        else {
+                            temp = (-bq[q] + sq) / a;
+                            if (temp < lim && temp > t_min) { lim = temp; key = make_key(temp, j + 2 * q, 0); }
+                        }
+                    }
+                }
+            }
         }
+#pragma unroll 1
+        for (; j < end; j += 2) {
+            const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
+            const float4 A2 = __ldg(&S.recs[j + 1].a);
+            float t;
+            if (hit_sphere(moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time), A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
+        }
+        if (COUNT) cnt.prim_tests += nrec >> 1;
     } else {  // K_RUN_BOX, PSC/box.h:23-38
 #pragma unroll 2
         for (int j = first; j < end; ++j) {

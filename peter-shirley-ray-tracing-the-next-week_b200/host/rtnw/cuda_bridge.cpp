@@ -149,4 +149,26 @@ int install_cuda_bridge(int device, unsigned long long seed) {
 
 rtnw_ctx* bridge_context() { return g_ctx; }
 
+// The bridge keeps the flattened, uploaded form of every object a call was made on, keyed by the object's address.  An object
+// that is mutated (or freed and its address reused) after its first call must be dropped from that cache:
+void bridge_invalidate(const void* object) {
+    auto it = g_cache.find(object);
+    if (it == g_cache.end()) return;
+    if (it->second->dev) rtnw_scene_free(g_ctx, it->second->dev);
+    delete it->second;
+    g_cache.erase(it);
+}
+
+// drop every cached scene and the bridge's context (device memory is returned); the virtuals abort again until the next install
+void bridge_release() {
+    for (auto& kv : g_cache) {
+        if (kv.second->dev) rtnw_scene_free(g_ctx, kv.second->dev);
+        delete kv.second;
+    }
+    g_cache.clear();
+    if (g_ctx) rtnw_ctx_destroy(g_ctx);
+    g_ctx = nullptr;
+    set_device_bridge(device_bridge());
+}
+
 }  // namespace rtnw

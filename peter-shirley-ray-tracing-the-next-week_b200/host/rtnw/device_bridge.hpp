@@ -20,6 +20,10 @@ void set_device_bridge(const device_bridge& b);
 const device_bridge& get_device_bridge();
 // defined in cuda_bridge.cpp (programs that link librtnw.so): serve the four virtuals from GPU `device`
 int install_cuda_bridge(int device, unsigned long long seed = 1);
+// the bridge caches the device form of every object a call was made on (by address): worlds must not change after their first
+// call, or be dropped with bridge_invalidate(object); bridge_release() frees every cached scene and the bridge's context
+void bridge_invalidate(const void* object);
+void bridge_release();
 }  // namespace rtnw
 
 #endif

@@ -50,6 +50,8 @@ static int selftest_bridge() {
     const vec3 nv = noise_texture(4).value(0, 0, vec3(1, 2, 3));
     std::printf("checker %g %g %g | %g %g %g\nnoise %.9g\nradiance %g %g %g\n", c0.x(), c0.y(), c0.z(), c1.x(), c1.y(), c1.z(), nv.x(),
                 radiance.x(), radiance.y(), radiance.z());
+    rtnw::bridge_invalidate(world);
+    rtnw::bridge_release();
     return 0;
 }
 
