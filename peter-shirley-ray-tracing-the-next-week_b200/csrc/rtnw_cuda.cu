@@ -707,7 +707,7 @@ struct stream_builder {
 
     // bvh_node `idx` with own box [bmin,bmax]: its leaves go to the record stream in left-to-right order (the key's tie
     // rule relies on it); every leaf child becomes (part of) a gate guarded by THIS node's box.
-    bool collect_gates(int32_t idx, const float* bmin, const float* bmax, int depth, std::vector<int>& mine) {
+    bool collect_gates(int32_t idx, const float* bmin, const float* bmax, int depth, std::vector<int>& mine, std::vector<int>& fmine) {
         if (idx < 0 || idx >= d.n_nodes) return bad("BVH node index out of range");
         if (depth > 4096) return bad("BVH deeper than 4096 levels (cycle?)");
         if (node_seen[idx]) return bad("BVH node referenced twice");
@@ -724,12 +724,27 @@ struct stream_builder {
         for (int w = 0; w < 2; ++w) {
             if (child[w] == RTNW_REF_NONE) continue;
             if (child[w] >= 0) {
-                if (!collect_gates(child[w], cmin[w], cmax[w], depth + 1, mine)) return false;
+                if (!collect_gates(child[w], cmin[w], cmax[w], depth + 1, mine, fmine)) return false;
             } else {
                 const size_t first = recs.size();
                 if (!emit_prims(~child[w], cnt[w], false, false)) return false;
                 if (recs.size() == first) return bad("empty BVH leaf");
                 (g.leaf0 < 0 ? g.leaf0 : g.leaf1) = (int32_t)first;
+                // RTNW_F_FAST_BVH: the leaf behind its OWN box (the reference's bounding_box of it, slightly padded: a primitive test
+                // in float32 can accept a ray that a tight float32 slab test of its box rejects, within rounding of the silhouette)
+                gate_t f;
+                float side = 0.f, reach = 0.f;
+                for (int a = 0; a < 3; ++a) {
+                    side = std::fmax(side, cmax[w][a] - cmin[w][a]);
+                    reach = std::fmax(reach, std::fmax(std::fabs(cmin[w][a]), std::fabs(cmax[w][a])));
+                }
+                const float pad = side * (1.0f / 1024.0f) + reach * (1.0f / 131072.0f);
+                for (int a = 0; a < 3; ++a) { f.bmin[a] = cmin[w][a] - pad; f.bmax[a] = cmax[w][a] + pad; }
+                f.leaf0 = (int32_t)first;
+                f.leaf1 = -1;
+                fmine.push_back((int)gates.size());
+                gates.push_back(f);
+                gate_leaves.push_back(make_int2(f.leaf0, -1));
             }
         }
         if (g.leaf0 >= 0) {
@@ -835,17 +850,22 @@ struct stream_builder {
         return (int)me;
     }
     // one BVH item: returns the root wide node and the depth of its gate tree
-    bool emit_bvh_item(const rtnw_item& it, int& root_out, int& depth_out) {
-        std::vector<int> mine;
-        if (!collect_gates(it.first, it.bmin, it.bmax, 0, mine)) return false;
+    // one BVH item: the root wide node and the depth of its gate tree (reference-exact traversal) and of the tree over its
+    // leaves' own boxes (RTNW_F_FAST_BVH)
+    bool emit_bvh_item(const rtnw_item& it, int& root_out, int& depth_out, int& froot_out, int& fdepth_out) {
+        std::vector<int> mine, fmine;
+        if (!collect_gates(it.first, it.bmin, it.bmax, 0, mine, fmine)) return false;
         if (mine.empty()) return bad("BVH without leaves");
-        std::vector<bin_node> bt;
-        bt.reserve(2 * mine.size());
-        const int broot = build_binary(mine, 0, mine.size(), bt);
-        max_wide_depth = 0;
-        root_out = emit_wide(bt, broot, 0);
-        depth_out = max_wide_depth + 1;
-        if (2 * RTNW_GROUP + 3 * depth_out + 8 > group_smem::QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
+        for (int pass = 0; pass < 2; ++pass) {
+            std::vector<int>& ids = pass ? fmine : mine;
+            std::vector<bin_node> bt;
+            bt.reserve(2 * ids.size());
+            const int broot = build_binary(ids, 0, ids.size(), bt);
+            max_wide_depth = 0;
+            (pass ? froot_out : root_out) = emit_wide(bt, broot, 0);
+            (pass ? fdepth_out : depth_out) = max_wide_depth + 1;
+            if (2 * RTNW_GROUP + 3 * (max_wide_depth + 1) + 8 > group_smem::QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
+        }
         return true;
     }
 
@@ -889,10 +909,12 @@ struct stream_builder {
             if (it.kind == RTNW_ITEM_PRIMS) {
                 if (!emit_prims(it.first, it.count, true, false, /*allow_runs=*/true)) return false;
             } else if (it.kind == RTNW_ITEM_BVH) {
-                int wroot = 0, wdepth = 0;
-                if (!emit_bvh_item(it, wroot, wdepth)) return false;  // leaves -> record stream, gates + gate tree -> side tables
+                int wroot = 0, wdepth = 0, froot = 0, fdepth = 0;
+                if (!emit_bvh_item(it, wroot, wdepth, froot, fdepth)) return false;  // leaves -> record stream, gates + trees -> side tables
                 recs[at].a.y = bits(wroot);
                 recs[at].a.z = bits(wdepth);
+                recs[at].a.w = bits(froot);   // RTNW_F_FAST_BVH: tree over the leaves' own boxes
+                recs[at].b.x = bits(fdepth);
             } else {
                 return bad("unknown item kind");
             }

@@ -702,33 +702,35 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
             const int room_ = (QN - n - 3 * tree_depth) / 3;
             const int take_ = (queued > QL - 4 * GROUP) ? 0 : min(min(n, GROUP), max(room_, 1));
             const int nt_ = (take_ + 31) & ~31;
-            const int drain_ = min(queued, (GROUP - nt_) >> 1);
+            const int drain_ = min(queued, FAST ? GROUP - nt_ : (GROUP - nt_) >> 1);  // exact mode: two lanes per gate, one per leaf
             sm.plan = make_int4(take_, n - take_, nt_, drain_);
             sm.n[nxt] = n - take_; sm.lh[nxt] = lh + (unsigned)drain_;  // pop both
         }
         group_sync<GROUP>();
         const int4 pl = sm.plan;
         const int take = pl.x, base = pl.y, node_threads = pl.z, drain = pl.w;
+        constexpr int LPG = FAST ? 1 : 2, LSH = FAST ? 0 : 1;  // lanes per gate: the fast mode's gates guard ONE leaf each
         uint32_t task = 0;
         if (tid < take) task = sm.q[base + tid];
-        else if (tid >= node_threads && tid - node_threads < 2 * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> 1)) & (QL - 1))];
+        else if (tid >= node_threads && tid - node_threads < LPG * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> LSH)) & (QL - 1))];
 #else
         // node tasks this round: none while the gate ring is nearly full; otherwise as many as the stack has room for
         const int room = (QN - n - 3 * tree_depth) / 3;
         const int take = (queued > QL - 4 * GROUP) ? 0 : min(min(n, GROUP), max(room, 1));
         const int base = n - take;
         const int node_threads = (take + 31) & ~31;
-        const int drain = min(queued, (GROUP - node_threads) >> 1);  // gates taken this round: TWO lanes each, one per leaf
+        constexpr int LPG = FAST ? 1 : 2, LSH = FAST ? 0 : 1;
+        const int drain = min(queued, (GROUP - node_threads) >> LSH);  // gates taken this round: TWO lanes each, one per leaf (fast mode: one)
         uint32_t task = 0;
         if (tid < take) task = sm.q[base + tid];
-        else if (tid >= node_threads && tid - node_threads < 2 * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> 1)) & (QL - 1))];
+        else if (tid >= node_threads && tid - node_threads < LPG * drain) task = sm.q[QN + ((lh + (unsigned)((tid - node_threads) >> LSH)) & (QL - 1))];
         if (tid == 0) { sm.n[nxt] = base; sm.lh[nxt] = lh + (unsigned)drain; }  // pop both
 #endif
 #ifdef RTNW_ROUND_STATS
         if (tid == 0) {
             RTNW_STAT(0, 1); RTNW_STAT(1, take); RTNW_STAT(2, drain); RTNW_STAT(8, n); RTNW_STAT(9, queued);
             if (take == 0) RTNW_STAT(3, 1);
-            const int busy = node_threads + 2 * drain;
+            const int busy = node_threads + LPG * drain;
             RTNW_STAT(busy <= 64 ? 4 : busy <= 128 ? 5 : busy <= 192 ? 6 : 7, 1);
             stat_busy = busy; stat_c = clock64();
         }
@@ -825,11 +827,11 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
                 base_n += __popc(bn[j]); base_l += (unsigned)__popc(bl[j]);
             }
             if (!ok) sm.overflow = 1;
-        } else if (tid - node_threads < 2 * drain) {
+        } else if (tid - node_threads < LPG * drain) {
             // ---- gate lanes: leaf->hit(r, tmin, tmax0) for the one or two leaves the gate guards, one lane per leaf (a leaf
             // test is about as long as a node task; a round lasts as long as its slowest lane)
             const int2 g = __ldg(&S.gates[RTNW_TASK_IDX(task)]);
-            const int leaf = (tid & 1) ? g.y : g.x;  // node_threads is even: lane parity = leaf of the gate
+            const int leaf = (!FAST && (tid & 1)) ? g.y : g.x;  // node_threads is even: lane parity = leaf of the gate
             hkey_t k = RTNW_KEY_NONE;
             if (leaf >= 0) {
                 const float4 A0 = __ldg(&S.recs[leaf].a), B0 = __ldg(&S.recs[leaf].b);
@@ -1147,8 +1149,8 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, SM& sm, 
                 sm.ray_o[v] = make_float4(r.o.x, r.o.y, r.o.z, key_t_or(sm.key[tid], t_max));
                 sm.ray_d[v] = make_float4(r.d.x, r.d.y, r.d.z, dot(r.d, r.d));
                 sm.ray_i[v] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-                if (nf == 0) root0 = __float_as_int(IA.y); else root1 = __float_as_int(IA.y);
-                depth = max(depth, __float_as_int(IA.z));
+                if (nf == 0) root0 = __float_as_int(IA.w); else root1 = __float_as_int(IA.w);  // the trees over the leaves' own boxes
+                depth = max(depth, __float_as_int(IB.x));
                 ++nf;
             }
             if (nf == SM::NFRAMES || (end && nf > 0)) {

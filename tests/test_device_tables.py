@@ -31,12 +31,13 @@ def _tables(name):
     return hs, t
 
 
-def _items(t):
-    """(record index, next, root, depth, is_bvh) of the top-level list's items"""
+def _items(t, fast=False):
+    """(record index, next, root, depth, is_bvh) of the top-level list's items; fast=True: root / depth of the tree over the
+    leaves' own boxes (RTNW_F_FAST_BVH) instead of the gate tree"""
     out, i = [], 0
     while (t["tag"][i] & 15) == K_ITEM:
-        a = t["recs"][i, :3].copy().view(np.int32)
-        out.append((i, int(a[0]), int(a[1]), int(a[2]), int(t["ival"][i]) == 1))
+        a = t["recs"][i, :5].copy().view(np.int32)
+        out.append((i, int(a[0]), int(a[3] if fast else a[1]), int(a[4] if fast else a[2]), int(t["ival"][i]) == 1))
         i = int(a[0])
     assert (t["tag"][i] & 15) == K_END and i == len(t["recs"]) - 1
     return out
@@ -113,7 +114,26 @@ def test_gates_and_gate_tree_structure(name):
             kind = int(t["tag"][j] & 15)
             assert j in covered, (name, j)
             j += 2 if kind == K_MSPHERE else (1 + int(t["recs"][j, 2:3].copy().view(np.int32)[0]) if kind == K_MEDIUM else 1)
-    assert gates_seen == set(range(len(t["gates"]))) or (len(t["gates"]) == 1 and int(t["gates"][0, 0]) == -1)
+    # the second tree of every BVH item (RTNW_F_FAST_BVH): one gate per leaf behind the leaf's own (padded) box, every leaf
+    # exactly once, interior boxes again exact unions; both trees together use every gate and every wide node of the tables
+    fast_gates, fast_leaves = set(), set()
+    for i, nxt, root, depth, is_bvh in _items(t, fast=True):
+        if not is_bvh:
+            continue
+        mine = set()
+        _, _, deepest = _subtree(t, root, 1, mine, nodes_seen)
+        assert deepest <= depth and not (mine & gates_seen) and not (mine & fast_gates)
+        for g in mine:
+            l0, l1 = (int(x) for x in t["gates"][g])
+            assert l1 == -1 and i < l0 < nxt and l0 not in fast_leaves
+            fast_leaves.add(l0)
+        fast_gates |= mine
+    exact_leaves = set()
+    for g in gates_seen:
+        l0, l1 = (int(x) for x in t["gates"][g])
+        exact_leaves |= {l0} | ({l1} if l1 >= 0 else set())
+    assert hs.desc.n_nodes == 0 or fast_leaves == exact_leaves
+    assert (gates_seen | fast_gates) == set(range(len(t["gates"]))) or (len(t["gates"]) == 1 and int(t["gates"][0, 0]) == -1)
     assert nodes_seen == set(range(len(t["wnodes"])))
     assert hs.desc.n_nodes == 0 or len(gates_seen) > 0
 
