@@ -620,18 +620,9 @@ struct coop_smem {
 #ifndef RTNW_ASYNC
 #define RTNW_ASYNC 0
 #endif
-#ifndef RTNW_POOL_SLEEP
-#define RTNW_POOL_SLEEP 32
-#endif
-#if RTNW_ASYNC == 2      // pooled form (pool_bvh_item): the shared rings ARE the queues, private stacks only take what does not fit
-#define RTNW_ANW 128
-#define RTNW_AGW 128
-#define RTNW_ARING 2048
-#else
 #define RTNW_ANW 256     // private node-task stack of a warp
 #define RTNW_AGW 256     // private gate-task stack of a warp
 #define RTNW_ARING 1024  // shared ring (one for node tasks, one for gate tasks), a power of two
-#endif
 #define RTNW_EMPTY 0xffffffffu
 // task = virtual slot (frame * GROUP + owner, 10 bits) | signs of the ray's direction in that frame (3 bits) | wide node
 // index or gate index (19 bits)
@@ -1066,190 +1057,6 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, SM& sm, int 
     group_sync<GROUP>();  // every candidate has been merged into sm.key before any owner reads its result
 }
 
-// ---- pooled warp-asynchronous BVH item (RTNW_ASYNC == 2) --------------------------------------------------------
-// async_bvh_item with the sharing turned around: the two shared rings are the block's task pool — every warp pushes the
-// children it finds straight into them and pops its next batch of 32 node tasks / 16 gates from them, so batches are full
-// as long as the block has work — and a warp's private stacks only take what a full ring cannot (bounded as before: a
-// batch shrinks as the private stack fills).  Reservation of ring space is exact (compare-and-swap on the tail), a slot is
-// handed over through its content (RTNW_EMPTY = not yet written / already taken).  No barrier inside the item.
-template <int GROUP, class SM>
-__device__ __forceinline__ bool ring_reserve(SM& sm, int which, int count, unsigned lane, unsigned& base) {
-    constexpr unsigned FULL = 0xffffffffu;
-    int ok = 0;
-    unsigned t = 0;
-    if (lane == 0) {
-        for (;;) {
-            t = ld_vol(&sm.ring_tail[which]);
-            if ((int)(t - ld_vol(&sm.ring_head[which])) + count > RTNW_ARING) break;
-            if (atomicCAS(&sm.ring_tail[which], t, t + (unsigned)count) == t) { ok = 1; break; }
-        }
-    }
-    ok = __shfl_sync(FULL, ok, 0);
-    base = __shfl_sync(FULL, t, 0);
-    return ok != 0;
-}
-__device__ __forceinline__ void ring_put(uint32_t* ring, unsigned at, uint32_t task) {
-    volatile uint32_t* slot = ring + (at & (RTNW_ARING - 1));
-    while (*slot != RTNW_EMPTY) {}  // the previous lap's taker has not cleared it yet
-    *slot = task;
-}
-
-template <int GROUP, bool COUNT, class SM>
-__device__ __forceinline__ void pool_bvh_item(const scene_view& S, SM& sm, int root, int tree_depth, bool active,
-                                              float t_min, uint32_t k0, uint32_t k1, trav_counters& cnt, int& phase) {
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr int NWARP = GROUP / 32, NW = RTNW_ANW, GW = RTNW_AGW;
-    const int tid = threadIdx.x % GROUP;
-    const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
-    const int warp = tid >> 5;
-    uint32_t* const myN = sm.q + warp * (NW + GW);
-    uint32_t* const myG = myN + NW;
-    uint32_t* const ringN = sm.q + NWARP * (NW + GW);
-    uint32_t* const ringG = ringN + RTNW_ARING;
-    const int ph = phase & 1;
-    if (tid == 0) sm.idle[ph ^ 1] = 0;
-    int nN = 0, nG = 0;
-    {   // one task per ray: the root of the gate tree, into the pool (or the private stack when the ring is full)
-        const unsigned b = __ballot_sync(FULL, active);
-        const int cnt_roots = __popc(b);
-        uint32_t t0 = 0;
-        if (active) {
-            const float4 ri = sm.ray_i[tid];
-            t0 = RTNW_TASK(tid, root) | (((ri.x < 0.f ? 1u : 0u) | (ri.y < 0.f ? 2u : 0u) | (ri.z < 0.f ? 4u : 0u)) << RTNW_IDX_BITS);
-        }
-        unsigned base = 0;
-        __threadfence_block();  // this warp's ray state is visible before its tasks are
-        if (cnt_roots && ring_reserve<GROUP, SM>(sm, 0, cnt_roots, lane, base)) {
-            if (active) ring_put(ringN, base + (unsigned)__popc(b & lt_mask), t0);
-        } else if (cnt_roots) {
-            if (active) myN[__popc(b & lt_mask)] = t0;
-            nN = cnt_roots;
-        }
-    }
-    __syncwarp();
-    bool idle = false;
-#pragma unroll 1
-    for (;;) {
-        // ---- what next: private leftovers first, then the pool (decided by lane 0, broadcast)
-        int kind = 0;  // 1 node batch, 2 gate batch, 0 nothing
-        if (nG >= 16 || (nG > 0 && nN == 0)) kind = 2;
-        else if (nN > 0) kind = 1;
-        if (kind == 0) {
-            int st = 0;  // 0 wait, 1 nodes in the pool, 2 gates in the pool, 3 every warp idle
-            if (lane == 0) {
-                const int an = (int)(ld_vol(&sm.ring_tail[0]) - ld_vol(&sm.ring_head[0]));
-                const int ag = (int)(ld_vol(&sm.ring_tail[1]) - ld_vol(&sm.ring_head[1]));
-                if (an >= 32 || (an > 0 && ag < 16)) st = 1;
-                else if (ag > 0) st = 2;
-                else if (idle && ld_vol(&sm.idle[ph]) == NWARP) st = 3;
-                if ((st == 1 || st == 2) && idle) atomicSub(&sm.idle[ph], 1);  // leave the idle state BEFORE taking a task
-                if (st == 0 && !idle) atomicAdd(&sm.idle[ph], 1);
-                if (st == 0) __nanosleep(RTNW_POOL_SLEEP);
-            }
-            st = __shfl_sync(FULL, st, 0);
-            if (st == 3) break;
-            if (st == 0) { idle = true; continue; }
-            if (idle) { __threadfence_block(); idle = false; }
-            kind = st;
-        }
-        if (kind == 1) {
-            // ---- node batch
-            const int room = (NW - nN - 3 * tree_depth) / 3;
-            const int cap = min(32, min(max(room, 1), (GW - nG) >> 2));  // what the private stacks can absorb if the rings are full
-            int take = min(nN, cap);
-            if (take == nN && take < cap) {  // from the pool / top the private batch up from it
-                const int got = ring_steal<GROUP, SM>(sm, ringN, 0, cap - take, myN + nN, lane);
-                if (got) __threadfence_block();
-                nN += got; take += got;
-            }
-            if (take == 0) continue;  // somebody else was faster
-            const bool live = (int)lane < take;
-            const uint32_t task = live ? myN[nN - take + (int)lane] : 0u;
-            nN -= take;
-            RTNW_STAT(0, 1); RTNW_STAT(1, take);
-            const int slot = RTNW_TASK_SLOT(task);
-            const float4* N = S.wnodes + 8 * (size_t)RTNW_TASK_IDX(task);
-            const float4 rf = __ldg(N + 6);
-            const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
-            const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
-            const int ref[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
-            const float t_hi = ro.w;
-            const unsigned sg = task >> RTNW_IDX_BITS;
-            const float4 nx4 = __ldg(N + ((sg & 1u) ? 3 : 0)), fx4 = __ldg(N + ((sg & 1u) ? 0 : 3));
-            const float4 ny4 = __ldg(N + ((sg & 2u) ? 4 : 1)), fy4 = __ldg(N + ((sg & 2u) ? 1 : 4));
-            const float4 nz4 = __ldg(N + ((sg & 4u) ? 5 : 2)), fz4 = __ldg(N + ((sg & 4u) ? 2 : 5));
-#define RTNW_SLAB(c) (!(fminf(fminf(fminf((fx4.c - o.x) * inv.x, t_hi), (fy4.c - o.y) * inv.y), (fz4.c - o.z) * inv.z) <= \
-                        fmaxf(fmaxf(fmaxf((nx4.c - o.x) * inv.x, t_min), (ny4.c - o.y) * inv.y), (nz4.c - o.z) * inv.z)) || (t_hi != t_hi))
-            bool pass[4];
-            pass[0] = live & (ref[0] != RTNW_REF_NONE) & RTNW_SLAB(x);
-            pass[1] = live & (ref[1] != RTNW_REF_NONE) & RTNW_SLAB(y);
-            pass[2] = live & (ref[2] != RTNW_REF_NONE) & RTNW_SLAB(z);
-            pass[3] = live & (ref[3] != RTNW_REF_NONE) & RTNW_SLAB(w);
-#undef RTNW_SLAB
-            if (COUNT && live) cnt.box_tests += (ref[0] != RTNW_REF_NONE) + (ref[1] != RTNW_REF_NONE) + (ref[2] != RTNW_REF_NONE) + (ref[3] != RTNW_REF_NONE);
-            __syncwarp();  // every lane has read its task before the private stack is written
-            unsigned bn[4], bl[4];
-            int tn = 0, tl = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                bn[j] = __ballot_sync(FULL, pass[j] & (ref[j] >= 0));
-                bl[j] = __ballot_sync(FULL, pass[j] & (ref[j] < 0));
-                tn += __popc(bn[j]); tl += __popc(bl[j]);
-            }
-            unsigned base_n = 0, base_l = 0;
-            const bool pool_n = tn > 0 && ring_reserve<GROUP, SM>(sm, 0, tn, lane, base_n);
-            const bool pool_l = tl > 0 && ring_reserve<GROUP, SM>(sm, 1, tl, lane, base_l);
-            int at_n = 0, at_l = 0;
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool isn = ref[j] >= 0;
-                const int pn = at_n + __popc(bn[j] & lt_mask), pl = at_l + __popc(bl[j] & lt_mask);
-                const uint32_t child = RTNW_TASK(slot, isn ? ref[j] : ~ref[j]) | RTNW_TASK_SIGNS(task);
-                if (pass[j]) {
-                    if (isn) { if (pool_n) ring_put(ringN, base_n + (unsigned)pn, child); else if (nN + pn < NW) myN[nN + pn] = child; else ok = false; }
-                    else { if (pool_l) ring_put(ringG, base_l + (unsigned)pl, child); else if (nG + pl < GW) myG[nG + pl] = child; else ok = false; }
-                }
-                at_n += __popc(bn[j]); at_l += __popc(bl[j]);
-            }
-            if (!ok) sm.overflow = 1;
-            if (!pool_n) nN = min(nN + tn, NW);
-            if (!pool_l) nG = min(nG + tl, GW);
-            __syncwarp();
-        } else {
-            // ---- gate batch: 16 gates, one lane per leaf
-            int take = min(nG, 16);
-            if (nG == 0 || take < 16) {
-                const int got = ring_steal<GROUP, SM>(sm, ringG, 1, 16 - take, myG + nG, lane);
-                if (got) __threadfence_block();
-                nG += got; take += got;
-            }
-            if (take == 0) continue;
-            const bool live = (int)(lane >> 1) < take;
-            const uint32_t task = live ? myG[nG - take + (int)(lane >> 1)] : 0u;
-            nG -= take;
-            RTNW_STAT(2, 1); RTNW_STAT(3, take);
-            if (live) {
-                const int slot = RTNW_TASK_SLOT(task);
-                const int2 g = __ldg(&S.gates[RTNW_TASK_IDX(task)]);
-                const int leaf = (lane & 1) ? g.y : g.x;
-                if (leaf >= 0) {
-                    const float4 A0 = __ldg(&S.recs[leaf].a), B0 = __ldg(&S.recs[leaf].b);
-                    const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
-                    const uint4 mq = sm.mkey[slot];
-                    ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
-                    medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-                    const hkey_t k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, ro.w, mk, cnt);
-                    if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
-                }
-            }
-            __syncwarp();
-        }
-    }
-    phase++;
-    group_sync<GROUP>();  // every candidate has been merged into sm.key before any owner reads its result
-}
-
 // world->hit(r, t_min, t_max, rec) (PSC/main.cpp:27) for the rays of the block.  Must be called by all threads; a
 // thread without a ray passes active = false and still works on the other threads' BVH tasks.
 // One element of the top-level list that is a plain list of primitives: scanned by each owner in lockstep.
@@ -1298,10 +1105,7 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, SM& sm, 
                 sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
                 sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
                 sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
-#if RTNW_ASYNC == 2
-                __syncwarp();
-                pool_bvh_item<GROUP, COUNT, SM>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
-#elif RTNW_ASYNC
+#if RTNW_ASYNC
                 __syncwarp();
                 async_bvh_item<GROUP, COUNT, SM>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
 #else
