@@ -100,6 +100,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
 
     coop_init<RTNW_GROUP, SM>(sm);
     group_sync<RTNW_GROUP>();
+#if RTNW_SMEM_NODES
+    stage_top_nodes<RTNW_GROUP, FAST, SM>(P.S, sm);
+#endif
     int r3 = 0;  // index of the cooperative traversal's next round, mod 3 (coop_bvh_item)
 #ifdef RTNW_ROUND_STATS
     const long long t_start = clock64();
@@ -346,6 +349,9 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     cnt.box_tests = 0; cnt.prim_tests = 0;
     coop_init<RTNW_GROUP, SM>(sm);
     group_sync<RTNW_GROUP>();
+#if RTNW_SMEM_NODES
+    stage_top_nodes<RTNW_GROUP, FAST, SM>(S, sm);
+#endif
     int r3 = 0;
     const hkey_t key = coop_closest_hit<RTNW_GROUP, false, FAST, SM>(S, sm, r, active, t_min, t_max, mk, cnt, r3);
     if (!active) return;
@@ -703,7 +709,6 @@ struct stream_builder {
     std::vector<int2> gate_leaves;      // device table
     std::vector<float4> wnodes;         // device table, 8 float4 per wide node
     std::vector<uint8_t> node_seen;
-    int max_wide_depth = 0;
 
     // bvh_node `idx` with own box [bmin,bmax]: its leaves go to the record stream in left-to-right order (the key's tie
     // rule relies on it); every leaf child becomes (part of) a gate guarded by THIS node's box.
@@ -813,58 +818,87 @@ struct stream_builder {
         out[me] = nd;
         return me;
     }
-    // collapse the binary tree into 4-wide nodes: repeatedly open the child with the largest box
-    int emit_wide(const std::vector<bin_node>& bt, int root, int depth) {
-        if (depth > max_wide_depth) max_wide_depth = depth;
-        int kids[4], nk = 0;
-        if (bt[root].gate >= 0) kids[nk++] = root;
-        else { kids[nk++] = bt[root].left; kids[nk++] = bt[root].right; }
-        while (nk < 4) {
-            int pick = -1;
-            double area = -1;
-            for (int q = 0; q < nk; ++q)
-                if (bt[kids[q]].gate < 0 && half_area(bt[kids[q]].bmin, bt[kids[q]].bmax) > area) { area = half_area(bt[kids[q]].bmin, bt[kids[q]].bmax); pick = q; }
-            if (pick < 0) break;
-            const int open = kids[pick];
-            kids[pick] = bt[open].left;
-            kids[nk++] = bt[open].right;
+    // Collapse binary trees into 4-wide nodes (repeatedly open the child with the largest box) and number the nodes of a
+    // whole FOREST level by level: all roots first, then every tree's second level, and so on — so that the first M nodes of
+    // the forest are the top levels of every tree (what k_render can keep in shared memory, RTNW_SMEM_NODES).
+    struct tree_t { std::vector<bin_node> bt; int broot = 0; size_t item_rec = 0; int root = 0, depth = 0; };
+    void emit_forest(std::vector<tree_t>& forest) {
+        struct pend { int tree, bnode, depth; size_t parent; int slot; };
+        std::vector<pend> level, next;
+        for (size_t t = 0; t < forest.size(); ++t) level.push_back(pend{(int)t, forest[t].broot, 0, (size_t)-1, 0});
+        while (!level.empty()) {
+            next.clear();
+            for (const pend& p : level) {
+                const std::vector<bin_node>& bt = forest[p.tree].bt;
+                int kids[4], nk = 0;
+                if (bt[p.bnode].gate >= 0) kids[nk++] = p.bnode;
+                else { kids[nk++] = bt[p.bnode].left; kids[nk++] = bt[p.bnode].right; }
+                while (nk < 4) {
+                    int pick = -1;
+                    double area = -1;
+                    for (int q = 0; q < nk; ++q)
+                        if (bt[kids[q]].gate < 0 && half_area(bt[kids[q]].bmin, bt[kids[q]].bmax) > area) { area = half_area(bt[kids[q]].bmin, bt[kids[q]].bmax); pick = q; }
+                    if (pick < 0) break;
+                    const int open = kids[pick];
+                    kids[pick] = bt[open].left;
+                    kids[nk++] = bt[open].right;
+                }
+                const size_t me = wnodes.size() / 8;
+                wnodes.resize(wnodes.size() + 8, make_float4(0, 0, 0, 0));
+                if (p.parent == (size_t)-1) forest[p.tree].root = (int)me;
+                else (&wnodes[8 * p.parent + 6].x)[p.slot] = bits((int32_t)me);
+                forest[p.tree].depth = std::max(forest[p.tree].depth, p.depth + 1);
+                float v[6][4];
+                int32_t ref[4], lrec[4];
+                for (int q = 0; q < 4; ++q) {
+                    ref[q] = RTNW_REF_NONE;
+                    lrec[q] = -1;
+                    for (int a = 0; a < 6; ++a) v[a][q] = 0.f;
+                }
+                for (int q = 0; q < nk; ++q) {
+                    const bin_node& c = bt[kids[q]];
+                    for (int a = 0; a < 3; ++a) { v[a][q] = c.bmin[a]; v[3 + a][q] = c.bmax[a]; }
+                    if (c.gate >= 0) { ref[q] = ~c.gate; lrec[q] = gate_leaves[c.gate].x; }  // lrec: first record of the gate's first leaf (prefetch hint)
+                    else { ref[q] = 0; next.push_back(pend{p.tree, kids[q], p.depth + 1, me, q}); }  // patched when the child is numbered
+                }
+                for (int a = 0; a < 6; ++a) wnodes[8 * me + a] = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
+                wnodes[8 * me + 6] = make_float4(bits(ref[0]), bits(ref[1]), bits(ref[2]), bits(ref[3]));
+                wnodes[8 * me + 7] = make_float4(bits(lrec[0]), bits(lrec[1]), bits(lrec[2]), bits(lrec[3]));
+            }
+            level.swap(next);
         }
-        const size_t me = wnodes.size() / 8;
-        wnodes.resize(wnodes.size() + 8, make_float4(0, 0, 0, 0));
-        float v[6][4];
-        int32_t ref[4];
-        for (int q = 0; q < 4; ++q) {
-            ref[q] = RTNW_REF_NONE;
-            for (int a = 0; a < 6; ++a) v[a][q] = 0.f;
-        }
-        for (int q = 0; q < nk; ++q) {
-            const bin_node& c = bt[kids[q]];
-            for (int a = 0; a < 3; ++a) { v[a][q] = c.bmin[a]; v[3 + a][q] = c.bmax[a]; }
-            ref[q] = c.gate >= 0 ? ~c.gate : emit_wide(bt, kids[q], depth + 1);
-        }
-        for (int a = 0; a < 6; ++a) wnodes[8 * me + a] = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
-        wnodes[8 * me + 6] = make_float4(bits(ref[0]), bits(ref[1]), bits(ref[2]), bits(ref[3]));
-        int32_t lrec[4];  // gate children: first record of the gate's first leaf (prefetch hint), else -1
-        for (int q = 0; q < 4; ++q) lrec[q] = (ref[q] != RTNW_REF_NONE && ref[q] < 0) ? gate_leaves[~ref[q]].x : -1;
-        wnodes[8 * me + 7] = make_float4(bits(lrec[0]), bits(lrec[1]), bits(lrec[2]), bits(lrec[3]));
-        return (int)me;
     }
-    // one BVH item: returns the root wide node and the depth of its gate tree
-    // one BVH item: the root wide node and the depth of its gate tree (reference-exact traversal) and of the tree over its
-    // leaves' own boxes (RTNW_F_FAST_BVH)
-    bool emit_bvh_item(const rtnw_item& it, int& root_out, int& depth_out, int& froot_out, int& fdepth_out) {
+    std::vector<tree_t> exact_forest, fast_forest;  // per BVH item: the gate tree (reference-exact traversal) and the tree over
+                                                    // the leaves' own boxes (RTNW_F_FAST_BVH); numbered after the last item
+    int32_t fast_base = 0;                          // first wide node of the fast forest
+
+    // one BVH item: its leaves go to the record stream now, its two binary SAH trees are kept for emit_forest
+    bool emit_bvh_item(const rtnw_item& it, size_t item_rec) {
         std::vector<int> mine, fmine;
         if (!collect_gates(it.first, it.bmin, it.bmax, 0, mine, fmine)) return false;
         if (mine.empty()) return bad("BVH without leaves");
         for (int pass = 0; pass < 2; ++pass) {
             std::vector<int>& ids = pass ? fmine : mine;
-            std::vector<bin_node> bt;
-            bt.reserve(2 * ids.size());
-            const int broot = build_binary(ids, 0, ids.size(), bt);
-            max_wide_depth = 0;
-            (pass ? froot_out : root_out) = emit_wide(bt, broot, 0);
-            (pass ? fdepth_out : depth_out) = max_wide_depth + 1;
-            if (2 * RTNW_GROUP + 3 * (max_wide_depth + 1) + 8 > group_smem::QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
+            std::vector<tree_t>& forest = pass ? fast_forest : exact_forest;
+            forest.push_back(tree_t());
+            tree_t& T = forest.back();
+            T.item_rec = item_rec;
+            T.bt.reserve(2 * ids.size());
+            T.broot = build_binary(ids, 0, ids.size(), T.bt);
+        }
+        return true;
+    }
+    bool finish_forests() {
+        emit_forest(exact_forest);
+        fast_base = (int32_t)(wnodes.size() / 8);
+        emit_forest(fast_forest);
+        for (size_t t = 0; t < exact_forest.size(); ++t) {
+            const tree_t &E = exact_forest[t], &F = fast_forest[t];
+            if (2 * RTNW_GROUP + 3 * std::max(E.depth, F.depth) + 8 > group_smem::QN) return bad("gate tree deeper than the cooperative task stack can reserve for");
+            recs[E.item_rec].a.y = bits(E.root);
+            recs[E.item_rec].a.z = bits(E.depth);
+            recs[E.item_rec].a.w = bits(F.root);   // RTNW_F_FAST_BVH: tree over the leaves' own boxes
+            recs[E.item_rec].b.x = bits(F.depth);
         }
         return true;
     }
@@ -909,12 +943,7 @@ struct stream_builder {
             if (it.kind == RTNW_ITEM_PRIMS) {
                 if (!emit_prims(it.first, it.count, true, false, /*allow_runs=*/true)) return false;
             } else if (it.kind == RTNW_ITEM_BVH) {
-                int wroot = 0, wdepth = 0, froot = 0, fdepth = 0;
-                if (!emit_bvh_item(it, wroot, wdepth, froot, fdepth)) return false;  // leaves -> record stream, gates + trees -> side tables
-                recs[at].a.y = bits(wroot);
-                recs[at].a.z = bits(wdepth);
-                recs[at].a.w = bits(froot);   // RTNW_F_FAST_BVH: tree over the leaves' own boxes
-                recs[at].b.x = bits(fdepth);
+                if (!emit_bvh_item(it, at)) return false;  // leaves -> record stream now; gates + trees -> side tables (finish_forests)
             } else {
                 return bad("unknown item kind");
             }
@@ -922,6 +951,7 @@ struct stream_builder {
         }
         cur_item_xf = 0;
         push(make_float4(0, 0, 0, 0), 0, 0, RTNW_TAG(K_END, 0, 0, 0), 0, -1);
+        if (!finish_forests()) return false;
         if (recs.size() >= (1u << 24) || gates.size() >= (1u << RTNW_IDX_BITS) || wnodes.size() / 8 >= (1u << RTNW_IDX_BITS)) return bad("scene exceeds the record / gate index range");
         if (gate_leaves.empty()) gate_leaves.push_back(make_int2(-1, -1));
         if (wnodes.empty()) wnodes.resize(8, make_float4(0, 0, 0, 0));
@@ -1252,7 +1282,7 @@ struct rtnw_prepared {
     bool pinned = false;
     size_t bytes = 0;
     size_t o_recs = 0, o_leaf = 0, o_rxf = 0, o_nodes = 0, o_gates = 0, o_xf = 0, o_mat = 0, o_tex = 0, o_rv = 0, o_perm = 0, o_img = 0;
-    int32_t n_recs = 0, n_materials = 0, n_textures = 0;
+    int32_t n_recs = 0, n_materials = 0, n_textures = 0, n_wnodes = 0, fast_node_base = 0;
 };
 
 int rtnw_prepared_free(rtnw_prepared* p) {
@@ -1316,6 +1346,8 @@ int rtnw_scene_prepare(const rtnw_scene_desc* desc, rtnw_prepared** out) {
     std::memcpy(P->host + P->o_perm, perm.data(), sz_perm);
     if (sz_img) std::memcpy(P->host + P->o_img, desc->images, sz_img);
     P->n_recs = (int32_t)sb.recs.size();
+    P->n_wnodes = (int32_t)(sb.wnodes.size() / 8);
+    P->fast_node_base = sb.fast_base;
     P->n_materials = desc->n_materials;
     P->n_textures = desc->n_textures;
     *out = P;
@@ -1365,6 +1397,8 @@ int rtnw_scene_upload_prepared(rtnw_ctx* ctx, const rtnw_prepared* P, rtnw_scene
     s->view.perm = base + P->o_perm;
     s->view.images = base + P->o_img;
     s->view.n_recs = P->n_recs;
+    s->view.n_wnodes = P->n_wnodes;
+    s->view.fast_node_base = P->fast_node_base;
     s->view.n_materials = P->n_materials;
     s->view.n_textures = P->n_textures;
     *out = s;

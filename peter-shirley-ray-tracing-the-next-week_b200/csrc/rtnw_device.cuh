@@ -62,6 +62,7 @@ struct scene_view {
                                 // child refs (int4): >= 0 wide node, < 0 ~gate, RTNW_REF_NONE absent; last float4 unused
     const int2* gates;          // per gate: first records of the (one or two) leaves it guards, -1 = none
     int32_t n_recs, n_materials, n_textures;
+    int32_t n_wnodes, fast_node_base;  // wide nodes in the table; first node of the RTNW_F_FAST_BVH forest (the exact forest starts at 0)
 };
 
 // ------------------------------------------------------------------------------------------------ vec3
@@ -572,6 +573,9 @@ __device__ __forceinline__ void scan_run(const scene_view& S, int first, int nre
 #ifndef RTNW_MIGRATE
 #define RTNW_MIGRATE 0
 #endif
+#ifndef RTNW_SMEM_NODES
+#define RTNW_SMEM_NODES 0   // > 0: the first N wide nodes of the forest (its top levels: nodes are numbered level by level) are staged in
+#endif                      // shared memory once per block with one bulk-async copy (cp.async.bulk + mbarrier) and read from there
 #ifndef RTNW_SIGNLOAD
 #define RTNW_SIGNLOAD 1   // near / far planes of a node task loaded by the ray's signs (carried in the task word) instead of selected (0: round-1 form)
 #endif
@@ -605,6 +609,10 @@ struct coop_smem {
     float4 acc[GROUP];    // k_render: the owner's work item — xyz = sum of its finished samples, w = next sample index k (int bits)
     int4 span[GROUP];     // k_render: the owner's work item — x = first sample of its pixel in this call (s_begin), y = end index of
                           // its range, z = pixel, w = range
+#if RTNW_SMEM_NODES
+    float4 top[8 * RTNW_SMEM_NODES];   // top levels of the gate forest, staged by stage_top_nodes
+    unsigned long long top_mbar;       // mbarrier the bulk copy completes on
+#endif
     int bins[8];          // RTNW_MIGRATE: rays per shading class of the current round (zero between rounds)
     int4 plan;            // RTNW_PLAN1: the round's plan (take, base, node_threads, drain), computed by thread 0 alone
     hkey_t key[GROUP];
@@ -645,6 +653,39 @@ __device__ __forceinline__ void coop_init(SM& sm) {
     for (int i = tid; i < 2 * RTNW_ARING; i += GROUP) sm.q[(GROUP / 32) * (RTNW_ANW + RTNW_AGW) + i] = RTNW_EMPTY;
 #endif
 }
+
+#if RTNW_SMEM_NODES
+// Once per block: the top levels of the forest this kernel traverses go to shared memory with ONE bulk-async copy
+// (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier that every thread then waits on).
+template <int GROUP, bool FAST, class SM>
+__device__ __forceinline__ void stage_top_nodes(const scene_view& S, SM& sm) {
+    const int base = FAST ? S.fast_node_base : 0;
+    const int n = min(RTNW_SMEM_NODES, S.n_wnodes - base);
+    if (n <= 0) return;
+    const uint32_t bytes = (uint32_t)n * 128u;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&sm.top_mbar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.top[0]);
+    if (threadIdx.x % GROUP == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    group_sync<GROUP>();
+    if (threadIdx.x % GROUP == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(S.wnodes + 8 * (size_t)base), "r"(bytes), "r"(mbar) : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TOP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra TOP_DONE;\n"
+        "bra TOP_WAIT;\n"
+        "TOP_DONE:\n"
+        "}\n" ::"r"(mbar) : "memory");
+}
+#endif
 
 // Closest hit of the block's rays against the BVH item whose gate tree has root `root`.  Owners have already written
 // their ray to sm.ray_* / sm.mkey and their running key to sm.key.  Called by all threads.
@@ -745,8 +786,16 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
             // (no short-circuit): the four slab tests are independent and interleave; a lane of the last node warp
             // without a task reads node 0 / slot 0 and masks its results.
             const bool live = tid < take;
+#if RTNW_SMEM_NODES
+            const uint32_t nbase = FAST ? (uint32_t)S.fast_node_base : 0u;
+            const uint32_t nidx = live ? RTNW_TASK_IDX(task) : nbase;
+            const float4* N = (nidx - nbase) < (uint32_t)RTNW_SMEM_NODES ? sm.top + 8 * (nidx - nbase) : S.wnodes + 8 * (size_t)nidx;
+#define RTNW_LDN(p) (*(p))   // shared or global: a generic load
+#else
             const float4* N = S.wnodes + 8 * (size_t)(live ? RTNW_TASK_IDX(task) : 0u);
-            const float4 rf = __ldg(N + 6);
+#define RTNW_LDN(p) __ldg(p)
+#endif
+            const float4 rf = RTNW_LDN(N + 6);
             const float4 ro = sm.ray_o[slot], ri = sm.ray_i[slot];
             const f3 o = mk3(ro.x, ro.y, ro.z), inv = mk3(ri.x, ri.y, ri.z);
             const int ref[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
@@ -759,9 +808,9 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
             // first; the ray's three signs travel in the task word, so the near and far planes of the four boxes are simply
             // LOADED from the right rows of the node instead of selected value by value (24 selects per task)
             const unsigned sg = task >> RTNW_IDX_BITS;
-            const float4 nx4 = __ldg(N + ((sg & 1u) ? 3 : 0)), fx4 = __ldg(N + ((sg & 1u) ? 0 : 3));
-            const float4 ny4 = __ldg(N + ((sg & 2u) ? 4 : 1)), fy4 = __ldg(N + ((sg & 2u) ? 1 : 4));
-            const float4 nz4 = __ldg(N + ((sg & 4u) ? 5 : 2)), fz4 = __ldg(N + ((sg & 4u) ? 2 : 5));
+            const float4 nx4 = RTNW_LDN(N + ((sg & 1u) ? 3 : 0)), fx4 = RTNW_LDN(N + ((sg & 1u) ? 0 : 3));
+            const float4 ny4 = RTNW_LDN(N + ((sg & 2u) ? 4 : 1)), fy4 = RTNW_LDN(N + ((sg & 2u) ? 1 : 4));
+            const float4 nz4 = RTNW_LDN(N + ((sg & 4u) ? 5 : 2)), fz4 = RTNW_LDN(N + ((sg & 4u) ? 2 : 5));
 #define RTNW_SLAB(c) (!(fminf(fminf(fminf((fx4.c - o.x) * inv.x, t_hi), (fy4.c - o.y) * inv.y), (fz4.c - o.z) * inv.z) <= \
                         fmaxf(fmaxf(fmaxf((nx4.c - o.x) * inv.x, t_min), (ny4.c - o.y) * inv.y), (nz4.c - o.z) * inv.z)) || (t_hi != t_hi))
             pass[0] = live & (ref[0] != RTNW_REF_NONE) & RTNW_SLAB(x);
@@ -770,7 +819,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
             pass[3] = live & (ref[3] != RTNW_REF_NONE) & RTNW_SLAB(w);
 #undef RTNW_SLAB
 #else
-            const float4 mnx = __ldg(N), mny = __ldg(N + 1), mnz = __ldg(N + 2), mxx = __ldg(N + 3), mxy = __ldg(N + 4), mxz = __ldg(N + 5);
+            const float4 mnx = RTNW_LDN(N), mny = RTNW_LDN(N + 1), mnz = RTNW_LDN(N + 2), mxx = RTNW_LDN(N + 3), mxy = RTNW_LDN(N + 4), mxz = RTNW_LDN(N + 5);
             pass[0] = live & (ref[0] != RTNW_REF_NONE) & hit_aabb6(mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, o, inv, t_min, t_hi);
             pass[1] = live & (ref[1] != RTNW_REF_NONE) & hit_aabb6(mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, o, inv, t_min, t_hi);
             pass[2] = live & (ref[2] != RTNW_REF_NONE) & hit_aabb6(mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, o, inv, t_min, t_hi);
