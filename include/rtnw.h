@@ -238,6 +238,13 @@ int rtnw_ctx_info(rtnw_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t*
  * FP32-issue roofline the path is reported against (not part of the reference) */
 int rtnw_measure_fp32_peak(rtnw_ctx* ctx, float* tflops);
 
+/* device self-test of the kernels' division shortcut (IEEE quotients computed from the reciprocal a ray already carries for
+ * aabb::hit, PSC/aabb.h:38, instead of a second division): n random boxes / spheres / rays, including zeros, infinities, NaN
+ * and the whole exponent range, each tested through the shortcut and through the plain IEEE form.  out = {box mismatches,
+ * sphere mismatches, raw quotient mismatches, boxes that took the shortcut, sphere hits, box hits}; the first three must be 0.
+ * Not part of the reference. */
+int rtnw_selftest_recip(rtnw_ctx* ctx, uint64_t n, uint32_t seed, uint64_t out[6]);
+
 int rtnw_scene_upload(rtnw_ctx* ctx, const rtnw_scene_desc* desc, rtnw_scene** out);
 
 /* rtnw_scene_upload in two steps, for callers that upload the same scene repeatedly or to several devices: rtnw_scene_prepare

@@ -112,7 +112,7 @@ assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 48
 
 # every symbol include/rtnw.h and include/rtnw_host.h declare (tests check the libraries export all of them)
 DEVICE_SYMBOLS = ["rtnw_last_error", "rtnw_abi_version", "rtnw_device_count", "rtnw_ctx_create", "rtnw_ctx_destroy",
-                  "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_quantize_device", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
+                  "rtnw_ctx_info", "rtnw_measure_fp32_peak", "rtnw_selftest_recip", "rtnw_quantize_device", "rtnw_scene_upload", "rtnw_scene_free", "rtnw_render", "rtnw_render_device", "rtnw_trace",
                   "rtnw_eval_texture", "rtnw_eval_perlin", "rtnw_scatter", "rtnw_camera_rays", "rtnw_camera_get_rays", "rtnw_plan_sample_ranges",
                   "rtnw_scene_inspect", "rtnw_ctx_create_multi", "rtnw_ctx_destroy_multi", "rtnw_multi_device_count",
                   "rtnw_scene_upload_multi", "rtnw_scene_free_multi", "rtnw_render_multi", "rtnw_scene_prepare", "rtnw_prepared_bytes",
@@ -173,6 +173,7 @@ def device_lib() -> C.CDLL:
         L.rtnw_ctx_destroy.argtypes = [C.c_void_p]
         L.rtnw_ctx_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
         L.rtnw_measure_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.rtnw_selftest_recip.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
         L.rtnw_quantize_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.rtnw_plan_sample_ranges.argtypes = [C.POINTER(RenderParams), C.POINTER(C.c_int32), C.c_int32]
         L.rtnw_scene_inspect.argtypes = [C.POINTER(SceneDesc), C.c_int32, C.c_void_p, C.c_size_t]
@@ -332,6 +333,12 @@ class Context:
         v = C.c_float()
         _check_dev(device_lib().rtnw_measure_fp32_peak(self._h, C.byref(v)))
         return float(v.value)
+
+    def selftest_recip(self, n: int, seed: int = 1) -> dict:
+        """rtnw_selftest_recip: n random box / sphere / ray cases through the reciprocal shortcut and through the IEEE form."""
+        out = (C.c_uint64 * 6)()
+        _check_dev(device_lib().rtnw_selftest_recip(self._h, n, seed, out))
+        return dict(zip(("box_mismatch", "sphere_mismatch", "quotient_mismatch", "box_shortcut", "sphere_hits", "box_hits"), map(int, out)))
 
     def quantize_device(self, dev_ptr: int, nx: int, ny: int, ns: int, clamp255: bool = True) -> np.ndarray:
         """PSC/main.cpp:315-325 on the GPU from a device buffer of sums; returns (ny, nx, 3) int32, top row first."""

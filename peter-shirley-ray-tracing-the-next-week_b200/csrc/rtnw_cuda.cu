@@ -419,6 +419,91 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters) {
     if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;  // keeps the chains alive
 }
 
+// Self-test of the reciprocal shortcuts (rtnw_device.cuh, "IEEE quotients from a reciprocal"): every thread draws boxes,
+// spheres and rays — scene-like values, origins exactly on face planes, zero / tiny / huge direction components, NaN and
+// infinities, exponents over the whole float range — and compares hit_box<true> / hit_sphere_recip with the IEEE forms
+// bit for bit; plus raw quotients inside the guard.  out: {box mismatches, sphere mismatches, quotient mismatches,
+// boxes that took the reciprocal path, spheres tested with a positive discriminant, box hits}.
+__device__ __forceinline__ float selftest_float(uint32_t bits, uint32_t mode) {
+    const uint32_t sign = bits & 0x80000000u, man = bits & 0x7fffffu;
+    switch (mode & 7u) {
+        case 0: return __uint_as_float(sign | ((100u + ((bits >> 23) & 63u)) << 23) | (0x7fffffu - (man & 0xffu)));  // mantissa near all ones
+        case 1: return __uint_as_float(sign | ((100u + ((bits >> 23) & 63u)) << 23) | (man & 0xffu));               // mantissa near 1.0
+        case 2: return __uint_as_float(bits);                                                                        // any float at all
+        case 3: return (bits & 1u) ? 0.0f : -0.0f;
+        default: return ((float)(int32_t)bits) * (1000.0f / 2147483648.0f);                                          // scene-like
+    }
+}
+__global__ void k_selftest_recip(uint64_t n, uint32_t seed, unsigned long long* out) {
+    unsigned long long bad_box = 0, bad_sph = 0, bad_div = 0, fast_box = 0, disc_pos = 0, box_hits = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 w[4];
+        for (uint32_t j = 0; j < 4; ++j) w[j] = philox_block((uint32_t)i, (uint32_t)(i >> 32), j, 0x5e1f7e57u, seed, 0u);
+        const uint32_t m = w[3].w;  // per-case mode word
+        // ---- raw quotient inside the guard: d and q within 2^+-40 / 2^80 is implied by exponents 100..163 both
+        {
+            const float x = selftest_float(w[0].x, (m >> 0) & 1u ? 0u : 1u), d = selftest_float(w[0].y, (m >> 1) & 1u ? 0u : 1u);
+            const float y = 1.0f / d;
+            const float xx = ((m >> 2) & 15u) == 0u ? 0.0f * x : x, q = div_by_recip(xx, d, y), ref = xx / d;
+            if (__float_as_uint(q) != __float_as_uint(ref) && !(q == 0.0f && ref == 0.0f)) ++bad_div;  // the sign of a zero quotient may differ
+        }
+        // ---- ray, box, sphere
+        const uint32_t vmode = ((m >> 6) & 3u) == 0u ? 2u : 4u;          // a quarter of the cases: any float at all
+        ray_t r;
+        r.o = mk3(selftest_float(w[0].z, vmode), selftest_float(w[0].w, vmode), selftest_float(w[1].x, vmode));
+        r.d = mk3(selftest_float(w[1].y, vmode), selftest_float(w[1].z, vmode), selftest_float(w[1].w, vmode));
+        r.time = 0.f;
+        if (((m >> 8) & 7u) == 0u) r.d.x = selftest_float(w[3].x, 3u);   // exact zeros
+        if (((m >> 11) & 7u) == 0u) r.d.y *= 1e-30f;                     // below the guard
+        if (((m >> 14) & 15u) == 0u) r.d.z *= 1e30f;                     // above the guard
+        f3 p0 = mk3(selftest_float(w[2].x, vmode), selftest_float(w[2].y, vmode), selftest_float(w[2].z, vmode));
+        f3 p1 = mk3(selftest_float(w[2].w, vmode), selftest_float(w[3].x, vmode), selftest_float(w[3].y, vmode));
+        if (p0.x > p1.x) { const float t = p0.x; p0.x = p1.x; p1.x = t; }
+        if (p0.y > p1.y) { const float t = p0.y; p0.y = p1.y; p1.y = t; }
+        if (p0.z > p1.z) { const float t = p0.z; p0.z = p1.z; p1.z = t; }
+        if (((m >> 18) & 3u) == 0u) r.o.y = p1.y;                        // the ray leaves a face of the box
+        if (((m >> 20) & 7u) == 0u) r.o.x = p0.x;
+        if (((m >> 23) & 1u) == 0u) {                                    // aim at the box so that hits are common
+            const float u = u01(w[3].z), v = u01(w[3].w), q = u01(w[1].x ^ w[2].y);
+            r.d = mk3(p0.x + u * (p1.x - p0.x), p0.y + v * (p1.y - p0.y), p0.z + q * (p1.z - p0.z)) - r.o;
+        }
+        const float t_lo = ((m >> 24) & 7u) == 0u ? 1e-12f : (((m >> 24) & 7u) == 1u ? 0.01f : 0.001f);
+        const float t_hi = ((m >> 27) & 1u) ? FLT_MAX : fabsf(selftest_float(w[3].z, 4u));
+        ray_recip rr;
+        rr.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+        const float a = dot(r.d, r.d);
+        rr.inv_a = 1.0f / a;
+        {
+            float ta = 0.f, tb = 0.f; int fa = 0, fb = 0; bool ieee = true;
+            const bool ha = hit_box<true>(p0, p1, r, rr, t_lo, t_hi, ta, fa, &ieee);
+            const bool hb = hit_box<false>(p0, p1, r, rr, t_lo, t_hi, tb, fb);
+            if (ha != hb || (ha && (__float_as_uint(ta) != __float_as_uint(tb) || fa != fb))) ++bad_box;
+#ifdef RTNW_SELFTEST_PRINT
+            if ((ha != hb || (ha && (__float_as_uint(ta) != __float_as_uint(tb) || fa != fb))) && bad_box <= 1 && blockIdx.x < 4 && threadIdx.x < 8)
+                printf("box o=(%a %a %a) d=(%a %a %a) p0=(%a %a %a) p1=(%a %a %a) tlo=%a thi=%a | recip hit=%d t=%a f=%d ieee=%d | ref hit=%d t=%a f=%d\n",
+                       r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, p0.x, p0.y, p0.z, p1.x, p1.y, p1.z, t_lo, t_hi, (int)ha, ta, fa, (int)ieee, (int)hb, tb, fb);
+#endif
+            if (!ieee) ++fast_box;
+            if (hb) ++box_hits;
+        }
+        {
+            const f3 c = 0.5f * (p0 + p1);
+            const float radius = 0.5f * fabsf(p1.x - p0.x);
+            float ta = 0.f, tb = 0.f;
+            const bool ha = hit_sphere_recip(c, radius, r, a, rr.inv_a, t_lo, t_hi, ta);
+            const bool hb = hit_sphere(c, radius, r, a, t_lo, t_hi, tb);
+            if (ha != hb || (ha && __float_as_uint(ta) != __float_as_uint(tb))) ++bad_sph;
+            if (hb) ++disc_pos;
+        }
+    }
+    if (bad_box) atomicAdd(&out[0], bad_box);
+    if (bad_sph) atomicAdd(&out[1], bad_sph);
+    if (bad_div) atomicAdd(&out[2], bad_div);
+    atomicAdd(&out[3], fast_box);
+    atomicAdd(&out[4], disc_pos);
+    atomicAdd(&out[5], box_hits);
+}
+
 __global__ void k_eval_texture(const scene_view S, int tex, const float* __restrict__ uvp, size_t n, float* __restrict__ rgb) {
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -1255,6 +1340,20 @@ int rtnw_measure_fp32_peak(rtnw_ctx* ctx, float* tflops) {
         if (rep > 0 && tf > best) best = tf;
     }
     *tflops = best;
+    return RTNW_OK;
+}
+
+int rtnw_selftest_recip(rtnw_ctx* ctx, uint64_t n, uint32_t seed, uint64_t out[6]) {
+    int rc = check_ctx(ctx);
+    if (rc != RTNW_OK) return rc;
+    if (!out) return fail(RTNW_ERR_INVALID, "null argument");
+    dev_buf d;
+    CUDA_TRY(d.alloc(6 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d.p, 0, 6 * sizeof(unsigned long long), ctx->stream));
+    k_selftest_recip<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(n, seed, d.as<unsigned long long>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return RTNW_OK;
 }
 

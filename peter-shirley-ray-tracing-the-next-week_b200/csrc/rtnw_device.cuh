@@ -175,6 +175,37 @@ __device__ __forceinline__ void xform_hit_back(const rtnw_xform_op* __restrict__
 // ------------------------------------------------------------------------------------------------ primitives
 // Each returns true and writes t when the reference's hit() would return true for (t_lo, t_hi).
 
+// RTNW_APPROX_PRIM is a measurement probe only ("filtered arithmetic"): MUFU-only square root and division in
+// the box (1) / sphere (2) / rectangle (4) tests — NOT bit-exact; it bounds from above what exact shortcuts can win.
+#ifndef RTNW_APPROX_PRIM
+#define RTNW_APPROX_PRIM 0
+#endif
+#define RTNW_DIVK(K, x, y) ((RTNW_APPROX_PRIM & (K)) ? __fdividef((x), (y)) : ((x) / (y)))
+#define RTNW_SQRTK(K, x) ((RTNW_APPROX_PRIM & (K)) ? ((x) * rsqrtf(x)) : sqrtf(x))
+
+// ---- IEEE quotients from a reciprocal the ray already carries
+// A BVH item keeps RN(1/d) per axis for aabb::hit (PSC/aabb.h:38) and, since every sphere divides by it, RN(1/dot(d,d)).
+// With y = RN(1/d):  q0 = RN(x*y) is within 2 ulp of x/d;  q1 = RN(q0 + RN(x - q0*d)*y) is faithful;  the residual
+// r = x - q1*d of a faithful quotient is exact in one FMA, and RN(q1 + r*y) = RN(x/d) (Markstein's theorem) — the bits an
+// IEEE division returns, in five dependent FMA-pipe instructions instead of MUFU.RCP + eight + a range check.  The theorem
+// needs every intermediate in the normal range.  The callers' guard: |d| within 2^+-40 and |x| <= 2^80 (fmaxf skips a NaN
+// x, whose quotient is the same canonical NaN either way) — then q*d and both residuals are finite, and they are normal
+// unless |x/d| < 2^-31, a quotient no caller looks at beyond `t < t_lo` / `t <= t_lo` with t_lo >= 2^-30 (also required),
+// which a wrong last bit or a wrong sign of zero cannot flip.  Outside the guard: the IEEE division.
+// tests/test_gpu_parity.py::test_division_by_reciprocal compares 2^30 pairs (random, extreme mantissas, zeros) bit for bit.
+#ifndef RTNW_RECIP
+#define RTNW_RECIP 1
+#endif
+struct ray_recip { f3 inv; float inv_a; };
+__device__ __forceinline__ float div_by_recip(float x, float d, float y) {
+    float q = x * y;
+    q = fmaf(fmaf(-q, d, x), y, q);
+    return fmaf(fmaf(-q, d, x), y, q);
+}
+#define RTNW_RECIP_DMIN 0x1p-40f
+#define RTNW_RECIP_DMAX 0x1p40f
+#define RTNW_RECIP_XMAX 0x1p80f
+#define RTNW_RECIP_TLO 0x1p-30f
 // PSC/sphere.h:25-52.  a = dot(d,d) is a pure function of the ray and is hoisted by the callers.
 __device__ __forceinline__ bool hit_sphere(f3 c, float radius, const ray_t& r, float a, float t_lo, float t_hi, float& t) {
     const f3 oc = r.o - c;
@@ -182,11 +213,29 @@ __device__ __forceinline__ bool hit_sphere(f3 c, float radius, const ray_t& r, f
     const float cc = dot(oc, oc) - radius * radius;
     const float disc = b * b - a * cc;
     if (disc > 0.f) {
+        const float sq = RTNW_SQRTK(2, disc);
+        float temp = RTNW_DIVK(2, -b - sq, a);
+        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
+        temp = RTNW_DIVK(2, -b + sq, a);
+        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
+    }
+    return false;
+}
+// the same with both roots divided through inv_a = RN(1/a)
+__device__ __forceinline__ bool hit_sphere_recip(f3 c, float radius, const ray_t& r, float a, float inv_a, float t_lo, float t_hi, float& t) {
+    const f3 oc = r.o - c;
+    const float b = dot(oc, r.d);
+    const float cc = dot(oc, oc) - radius * radius;
+    const float disc = b * b - a * cc;
+    if (disc > 0.f) {
         const float sq = sqrtf(disc);
-        float temp = (-b - sq) / a;
-        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
-        temp = (-b + sq) / a;
-        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
+        const float x0 = -b - sq, x1 = -b + sq;
+        float q0 = div_by_recip(x0, a, inv_a), q1 = div_by_recip(x1, a, inv_a);
+        if (!(a >= RTNW_RECIP_DMIN && a <= RTNW_RECIP_DMAX && fmaxf(fabsf(x0), fabsf(x1)) <= RTNW_RECIP_XMAX && t_lo >= RTNW_RECIP_TLO)) {
+            q0 = x0 / a; q1 = x1 / a;
+        }
+        if (q0 < t_hi && q0 > t_lo) { t = q0; return true; }
+        if (q1 < t_hi && q1 > t_lo) { t = q1; return true; }
     }
     return false;
 }
@@ -199,7 +248,7 @@ template <int N, int A, int B>
 __device__ __forceinline__ bool hit_rect(float a0, float a1, float b0, float b1, float k, const ray_t& r, float t_lo, float t_hi, float& t) {
     const float* o = &r.o.x;
     const float* d = &r.d.x;
-    const float tt = (k - o[N]) / d[N];
+    const float tt = RTNW_DIVK(4, k - o[N], d[N]);
     if (tt < t_lo || tt > t_hi) return false;
     const float a = o[A] + tt * d[A];
     const float b = o[B] + tt * d[B];
@@ -211,12 +260,27 @@ __device__ __forceinline__ bool hit_rect(float a0, float a1, float b0, float b1,
 // and extent tests do not depend on the narrowing limit, so they are evaluated first (independent IEEE divisions that
 // interleave); the list's sequential narrowing is then six compare/selects over the same predicates as hit_rect
 // (a NaN t passes every comparison exactly as there).
-__device__ __forceinline__ bool hit_box(f3 p0, f3 p1, const ray_t& r, float t_lo, float t_hi, float& t, int& face) {
+template <bool RECIP>
+__device__ __forceinline__ bool hit_box(f3 p0, f3 p1, const ray_t& r, const ray_recip& rr, float t_lo, float t_hi, float& t, int& face,
+                                        bool* took_ieee = nullptr) {
     float tt[6];
     bool in[6];
-    tt[0] = (p1.z - r.o.z) / r.d.z; tt[1] = (p0.z - r.o.z) / r.d.z;
-    tt[2] = (p1.y - r.o.y) / r.d.y; tt[3] = (p0.y - r.o.y) / r.d.y;
-    tt[4] = (p1.x - r.o.x) / r.d.x; tt[5] = (p0.x - r.o.x) / r.d.x;
+    const float x[6] = {p1.z - r.o.z, p0.z - r.o.z, p1.y - r.o.y, p0.y - r.o.y, p1.x - r.o.x, p0.x - r.o.x};
+    bool ieee = true;
+    if (RECIP) {
+        tt[0] = div_by_recip(x[0], r.d.z, rr.inv.z); tt[1] = div_by_recip(x[1], r.d.z, rr.inv.z);
+        tt[2] = div_by_recip(x[2], r.d.y, rr.inv.y); tt[3] = div_by_recip(x[3], r.d.y, rr.inv.y);
+        tt[4] = div_by_recip(x[4], r.d.x, rr.inv.x); tt[5] = div_by_recip(x[5], r.d.x, rr.inv.x);
+        const float dlo = fminf(fminf(fabsf(r.d.x), fabsf(r.d.y)), fabsf(r.d.z)), dhi = fmaxf(fmaxf(fabsf(r.d.x), fabsf(r.d.y)), fabsf(r.d.z));
+        const float xhi = fmaxf(fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))), fmaxf(fabsf(x[4]), fabsf(x[5])));
+        ieee = !(dlo >= RTNW_RECIP_DMIN && dhi <= RTNW_RECIP_DMAX && xhi <= RTNW_RECIP_XMAX && t_lo >= RTNW_RECIP_TLO);
+    }
+    if (took_ieee) *took_ieee = ieee;
+    if (ieee) {
+        tt[0] = RTNW_DIVK(1, x[0], r.d.z); tt[1] = RTNW_DIVK(1, x[1], r.d.z);
+        tt[2] = RTNW_DIVK(1, x[2], r.d.y); tt[3] = RTNW_DIVK(1, x[3], r.d.y);
+        tt[4] = RTNW_DIVK(1, x[4], r.d.x); tt[5] = RTNW_DIVK(1, x[5], r.d.x);
+    }
 #pragma unroll
     for (int f = 0; f < 2; ++f) {  // xy faces
         const float a = r.o.x + tt[f] * r.d.x, b = r.o.y + tt[f] * r.d.y;
@@ -252,39 +316,45 @@ struct surf_hit_t { float t; int face; };  // face < 0: miss
 #ifndef RTNW_SURFACE_INLINE
 #define RTNW_SURFACE_INLINE __forceinline__
 #endif
+template <bool RECIP>
 __device__ RTNW_SURFACE_INLINE surf_hit_t hit_surface_rec(const rec* __restrict__ recs, const rtnw_xform_op* __restrict__ xforms, int i, float4 A,
-                                                          float4 B, ray_t r, float a, float t_lo, float t_hi) {
+                                                          float4 B, ray_t r, float a, ray_recip rr, float t_lo, float t_hi) {
     const uint32_t tag = __float_as_uint(B.z);
     const uint32_t kind = tag & 15u;
     const uint32_t chain = tag >> 8;
     if (chain) {
         xform_ray(xforms, chain, r);
         a = dot(r.d, r.d);
+        if (RECIP) { rr.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z); rr.inv_a = 1.0f / a; }
     }
     surf_hit_t out;
     out.face = 0;
     out.t = 0.f;
     bool hit;
     switch (kind) {
-        case K_SPHERE: hit = hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_lo, t_hi, out.t); break;
+        case K_SPHERE:
+            hit = RECIP ? hit_sphere_recip(mk3(A.x, A.y, A.z), A.w, r, a, rr.inv_a, t_lo, t_hi, out.t)
+                        : hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_lo, t_hi, out.t);
+            break;
         case K_MSPHERE: {
             const float4 A2 = __ldg(&recs[i + 1].a);
             const f3 c = moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
-            hit = hit_sphere(c, A.w, r, a, t_lo, t_hi, out.t);
+            hit = RECIP ? hit_sphere_recip(c, A.w, r, a, rr.inv_a, t_lo, t_hi, out.t) : hit_sphere(c, A.w, r, a, t_lo, t_hi, out.t);
             break;
         }
         case K_RECT_XY: hit = hit_rect<2, 0, 1>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
         case K_RECT_XZ: hit = hit_rect<1, 0, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
         case K_RECT_YZ: hit = hit_rect<0, 1, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
-        case K_BOX: hit = hit_box(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, t_lo, t_hi, out.t, out.face); break;
+        case K_BOX: hit = hit_box<RECIP>(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, rr, t_lo, t_hi, out.t, out.face); break;
         default: hit = false; break;
     }
     if (!hit) out.face = -1;
     return out;
 }
+template <bool RECIP = false>
 __device__ __forceinline__ bool hit_surface(const scene_view& S, int i, float4 A, float4 B, uint32_t tag, const ray_t& r_frame,
-                                            float a_frame, float t_lo, float t_hi, float& t, int& face) {
-    const surf_hit_t h = hit_surface_rec(S.recs, S.xforms, i, A, B, r_frame, a_frame, t_lo, t_hi);
+                                            float a_frame, float t_lo, float t_hi, float& t, int& face, const ray_recip& rr = ray_recip()) {
+    const surf_hit_t h = hit_surface_rec<RECIP>(S.recs, S.xforms, i, A, B, r_frame, a_frame, rr, t_lo, t_hi);
     t = h.t;
     face = h.face < 0 ? 0 : h.face;
     return h.face >= 0;
@@ -401,9 +471,10 @@ __device__ __forceinline__ bool hit_aabb6(float mnx, float mny, float mnz, float
 }
 
 // One primitive record (surface or medium) of a scope whose narrowing limit is `lim`; returns records consumed.
-template <bool COUNT>
+template <bool COUNT, bool RECIP = false>
 __device__ __forceinline__ int test_record(const scene_view& S, int i, float4 A, float4 B, const ray_t& r, float a, float t_min,
-                                           float lim, const medium_key& mk, bool& hit, float& t, int& face, trav_counters& cnt) {
+                                           float lim, const medium_key& mk, bool& hit, float& t, int& face, trav_counters& cnt,
+                                           const ray_recip& rr = ray_recip()) {
     const uint32_t tag = __float_as_uint(B.z);
     const uint32_t kind = tag & 15u;
     if (COUNT) cnt.prim_tests++;
@@ -412,21 +483,21 @@ __device__ __forceinline__ int test_record(const scene_view& S, int i, float4 A,
         hit = hit_medium(S, i, A, tag, r, a, t_min, lim, mk, t);
         return 1 + __float_as_int(A.z);
     }
-    hit = hit_surface(S, i, A, B, tag, r, a, t_min, lim, t, face);
+    hit = hit_surface<RECIP>(S, i, A, B, tag, r, a, t_min, lim, t, face, rr);
     return kind == K_MSPHERE ? 2 : 1;
 }
 
 // A leaf of a bvh_node (one hitable, possibly a list of several primitives): tested with the UN-narrowed range the
 // node received, narrowing only inside the leaf (PSC/bvh.h:34-35, PSC/hitable_list.h:23-29).  Returns its candidate key.
 template <bool COUNT>
-__device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, float4 A, float4 B, const ray_t& r, float a, float t_min,
-                                            float tmax0, const medium_key& mk, trav_counters& cnt) {
+__device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, float4 A, float4 B, const ray_t& r, float a, const ray_recip& rr,
+                                            float t_min, float tmax0, const medium_key& mk, trav_counters& cnt) {
     hkey_t best = RTNW_KEY_NONE;
     float lim = tmax0;
     int i = first;  // A, B: record `first`, loaded by the caller (both leaves of a gate are fetched before either is tested)
     for (;;) {
         bool hit; float t; int face;
-        const int step = test_record<COUNT>(S, i, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
+        const int step = test_record<COUNT, RTNW_RECIP != 0>(S, i, A, B, r, a, t_min, lim, mk, hit, t, face, cnt, rr);
         if (hit) { lim = t; best = make_key(t, i, face); }  // inside a list the later accepted hit always replaces
         if (__float_as_uint(B.z) & RTNW_TAG_LAST) break;
         i += step;
@@ -531,7 +602,7 @@ __device__ __forceinline__ void scan_run(const scene_view& S, int first, int nre
         for (int j = first; j < end; ++j) {
             const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
             float t; int face = 0;
-            if (hit_box(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, t_min, lim, t, face)) { lim = t; key = make_key(t, j, face); }
+            if (hit_box<false>(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, ray_recip(), t_min, lim, t, face)) { lim = t; key = make_key(t, j, face); }
         }
         if (COUNT) cnt.prim_tests += nrec;
     }
@@ -604,8 +675,8 @@ struct coop_smem {
     // the RTNW_F_FAST_BVH kernels, which traverse two BVH items at once)
     float4 ray_o[FRAMES * GROUP];  // o.xyz in the item frame, w = tmax0 (closest_so_far when the item is entered)
     float4 ray_d[FRAMES * GROUP];  // d.xyz, w = dot(d,d)
-    float4 ray_i[FRAMES * GROUP];  // 1/d, w = time
-    uint4 mkey[GROUP];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media)
+    float4 ray_i[FRAMES * GROUP];  // 1/d, w = 1/dot(d,d)
+    uint4 mkey[GROUP];    // pixel, sample, depth of the owner's path (keys the free-flight draw of media), w = the ray's time
     float4 acc[GROUP];    // k_render: the owner's work item — xyz = sum of its finished samples, w = next sample index k (int bits)
     int4 span[GROUP];     // k_render: the owner's work item — x = first sample of its pixel in this call (s_begin), y = end index of
                           // its range, z = pixel, w = range
@@ -886,10 +957,11 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
                 const float4 A0 = __ldg(&S.recs[leaf].a), B0 = __ldg(&S.recs[leaf].b);
                 const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
                 const uint4 mq = sm.mkey[own];
-                ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+                ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = __uint_as_float(mq.w);
+                ray_recip rr; rr.inv = mk3(ri.x, ri.y, ri.z); rr.inv_a = ri.w;
                 medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
                 const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[own], ro.w)) : ro.w;
-                k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, t_hi, mk, cnt);
+                k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, rr, t_min, t_hi, mk, cnt);
             }
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[own], k);
         }
@@ -1084,9 +1156,10 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, SM& sm, int 
                     const float4 A0 = __ldg(&S.recs[leaf].a), B0 = __ldg(&S.recs[leaf].b);
                     const float4 ro = sm.ray_o[slot], rd = sm.ray_d[slot], ri = sm.ray_i[slot];
                     const uint4 mq = sm.mkey[slot];
-                    ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = ri.w;
+                    ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = __uint_as_float(mq.w);
+                    ray_recip rr; rr.inv = mk3(ri.x, ri.y, ri.z); rr.inv_a = ri.w;
                     medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-                    const hkey_t k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, t_min, ro.w, mk, cnt);
+                    const hkey_t k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, rr, t_min, ro.w, mk, cnt);
                     if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
                 }
             }
@@ -1137,7 +1210,7 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, SM& sm, 
                                                    float t_min, float t_max, const medium_key& mk, trav_counters& cnt, int& r3) {
     const int tid = threadIdx.x % GROUP;
     sm.key[tid] = RTNW_KEY_NONE;
-    sm.mkey[tid] = make_uint4(mk.pixel, mk.sample, mk.depth, 0u);
+    sm.mkey[tid] = make_uint4(mk.pixel, mk.sample, mk.depth, __float_as_uint(wr.time));
     if (!FAST) {
         int i = 0;
         for (;;) {  // the elements of the top-level hitable_list, in order (PSC/hitable_list.h:24-30); uniform over the block
@@ -1153,7 +1226,7 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, SM& sm, 
             if (__float_as_int(IB.w) == RTNW_ITEM_BVH) {
                 sm.ray_o[tid] = make_float4(r.o.x, r.o.y, r.o.z, best_t);
                 sm.ray_d[tid] = make_float4(r.d.x, r.d.y, r.d.z, a);
-                sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
+                sm.ray_i[tid] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, 1.0f / a);
 #if RTNW_ASYNC
                 __syncwarp();
                 async_bvh_item<GROUP, COUNT, SM>(S, sm, __float_as_int(IA.y), __float_as_int(IA.z), active, t_min, mk.k0, mk.k1, cnt, r3);
@@ -1196,8 +1269,9 @@ __device__ __forceinline__ hkey_t coop_closest_hit(const scene_view& S, SM& sm, 
                 xform_ray(S.xforms, tag >> 8, r);
                 const int v = nf * GROUP + tid;
                 sm.ray_o[v] = make_float4(r.o.x, r.o.y, r.o.z, key_t_or(sm.key[tid], t_max));
-                sm.ray_d[v] = make_float4(r.d.x, r.d.y, r.d.z, dot(r.d, r.d));
-                sm.ray_i[v] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, r.time);
+                const float a = dot(r.d, r.d);
+                sm.ray_d[v] = make_float4(r.d.x, r.d.y, r.d.z, a);
+                sm.ray_i[v] = make_float4(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z, 1.0f / a);
                 if (nf == 0) root0 = __float_as_int(IA.w); else root1 = __float_as_int(IA.w);  // the trees over the leaves' own boxes
                 depth = max(depth, __float_as_int(IB.x));
                 ++nf;

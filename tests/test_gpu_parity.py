@@ -530,3 +530,13 @@ def test_camera_get_ray_entry_point(rtnw, ctx):
             off = r["origin"] - org
             assert np.all(np.linalg.norm(off, axis=1) <= 1.0 + 1e-5) and np.linalg.norm(off, axis=1).max() > 0.9
             assert np.allclose(r["origin"] + r["direction"], target, rtol=1e-5, atol=1e-5)
+
+
+def test_division_by_reciprocal(ctx):
+    """The leaf tests of a BVH item divide through the reciprocals the ray carries for aabb::hit (rtnw_device.cuh,
+    div_by_recip): 2^30 random cases — scene-like values, rays leaving a face plane, zero / tiny / huge components, NaN,
+    infinities, any exponent — must give the bits of the IEEE division, as quotients and as hit_box / hit_sphere results."""
+    r = ctx.selftest_recip(1 << 30, seed=20261018)
+    assert r["box_mismatch"] == 0 and r["sphere_mismatch"] == 0 and r["quotient_mismatch"] == 0, r
+    # the shortcut, and real hits, must actually have been exercised
+    assert r["box_shortcut"] > (1 << 28) and r["box_hits"] > (1 << 26) and r["sphere_hits"] > (1 << 24), r
