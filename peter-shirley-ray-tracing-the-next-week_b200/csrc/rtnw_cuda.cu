@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK, RTNW_MIN_BLOCKS) k_render(const re
                     const uint32_t tk = __float_as_uint(__ldg(reinterpret_cast<const float4*>(P.S.textures + __float_as_int(m0.y))).x);
                     want_uv = tk == RTNW_TEX_IMAGE || tk == RTNW_TEX_CHECKER;
                 }
-                finish_hit(P.S, wr, h, s, want_uv);
+                finish_hit<FAST && RTNW_FAST_APPROX>(P.S, wr, h, s, want_uv);
                 if (__float_as_uint(m0.x) == RTNW_MAT_DIFFUSE_LIGHT) {  // the only material that emits; it never scatters
                     if (emit) L = L + T * texture_value(P.S, __float_as_int(m0.y), s.u, s.v, s.p);
                 } else if (depth < P.p.max_depth) {
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(RTNW_BLOCK) k_trace(const scene_view S, const 
     o.mat_id = -1;
     if (h.rec >= 0) {
         surf_t s;
-        finish_hit(S, r, h, s);
+        finish_hit<FAST && RTNW_FAST_APPROX>(S, r, h, s);
         o.prim_id = S.rec_leaf[h.rec];
         o.sub_id = h.face;
         o.t = h.t;
@@ -475,8 +475,8 @@ __global__ void k_selftest_recip(uint64_t n, uint32_t seed, unsigned long long* 
         rr.inv_a = 1.0f / a;
         {
             float ta = 0.f, tb = 0.f; int fa = 0, fb = 0; bool ieee = true;
-            const bool ha = hit_box<true>(p0, p1, r, rr, t_lo, t_hi, ta, fa, &ieee);
-            const bool hb = hit_box<false>(p0, p1, r, rr, t_lo, t_hi, tb, fb);
+            const bool ha = hit_box<ARITH_RECIP>(p0, p1, r, rr, t_lo, t_hi, ta, fa, &ieee);
+            const bool hb = hit_box<ARITH_IEEE>(p0, p1, r, rr, t_lo, t_hi, tb, fb);
             if (ha != hb || (ha && (__float_as_uint(ta) != __float_as_uint(tb) || fa != fb))) ++bad_box;
 #ifdef RTNW_SELFTEST_PRINT
             if ((ha != hb || (ha && (__float_as_uint(ta) != __float_as_uint(tb) || fa != fb))) && bad_box <= 1 && blockIdx.x < 4 && threadIdx.x < 8)
@@ -1213,6 +1213,8 @@ int render_finish(rtnw_ctx* ctx, const render_ticket& t, rtnw_stats* stats) {
                 (double)rs[4] / rs[0], (double)rs[5] / rs[0], (double)rs[6] / rs[0], (double)rs[7] / rs[0], rs[10], (double)rs[0] / rs[10],
                 (double)rs[11] / rs[12], (double)rs[14] / rs[12], (double)rs[13] / rs[12], (double)rs[15] / (rs[4] + 1), (double)rs[16] / (rs[5] + 1),
                 (double)rs[17] / (rs[6] + 1), (double)rs[18] / (rs[7] + 1), (double)rs[12] / rs[10]);
+        fprintf(stderr, "round_stats small: work<=32 %.3f of rounds, %.0f cycles each, %.3f of bvh cycles; work 33..64 %.3f of rounds, %.0f cycles each, %.3f of bvh cycles\n",
+                (double)rs[19] / rs[0], (double)rs[20] / (rs[19] + 1), (double)rs[20] / rs[14], (double)rs[21] / rs[0], (double)rs[22] / (rs[21] + 1), (double)rs[22] / rs[14]);
         unsigned long long z[32] = {0};
         cudaMemcpyToSymbol(g_round_stats, z, sizeof z);
     }

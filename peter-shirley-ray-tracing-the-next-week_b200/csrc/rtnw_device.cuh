@@ -196,6 +196,14 @@ __device__ __forceinline__ void xform_hit_back(const rtnw_xform_op* __restrict__
 #ifndef RTNW_RECIP
 #define RTNW_RECIP 1
 #endif
+// How a leaf test of a BVH item divides: the IEEE division, the exact shortcut above, or — experiment RTNW_FAST_APPROX=1,
+// RTNW_F_FAST_BVH kernels only — one multiplication by the reciprocal (<= 2 ulp; square roots as x * rsqrt(x)) with the
+// winner's t re-evaluated in IEEE form by finish_hit.  Measured +1.7 % (622 vs 612 Mpaths/s) with 1 of 580 519 closest hits
+// changing its t: within the flag's contract and north_star's 1e-5, but not worth giving up a bit-exact gate — off.
+#ifndef RTNW_FAST_APPROX
+#define RTNW_FAST_APPROX 0
+#endif
+enum { ARITH_IEEE = 0, ARITH_RECIP = 1, ARITH_APPROX = 2 };
 struct ray_recip { f3 inv; float inv_a; };
 __device__ __forceinline__ float div_by_recip(float x, float d, float y) {
     float q = x * y;
@@ -239,6 +247,21 @@ __device__ __forceinline__ bool hit_sphere_recip(f3 c, float radius, const ray_t
     }
     return false;
 }
+// RTNW_F_FAST_BVH: approximate roots (MUFU.RSQ, two multiplications); see ARITH_APPROX
+__device__ __forceinline__ bool hit_sphere_approx(f3 c, float radius, const ray_t& r, float a, float inv_a, float t_lo, float t_hi, float& t) {
+    const f3 oc = r.o - c;
+    const float b = dot(oc, r.d);
+    const float cc = dot(oc, oc) - radius * radius;
+    const float disc = b * b - a * cc;
+    if (disc > 0.f) {
+        const float sq = disc * rsqrtf(disc);
+        float temp = (-b - sq) * inv_a;
+        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
+        temp = (-b + sq) * inv_a;
+        if (temp < t_hi && temp > t_lo) { t = temp; return true; }
+    }
+    return false;
+}
 // PSC/sphere.h:81-83
 __device__ __forceinline__ f3 moving_center(f3 c0, f3 c1, float time0, float time1, float time) {
     return c0 + ((time - time0) / (time1 - time0)) * (c1 - c0);
@@ -260,14 +283,17 @@ __device__ __forceinline__ bool hit_rect(float a0, float a1, float b0, float b1,
 // and extent tests do not depend on the narrowing limit, so they are evaluated first (independent IEEE divisions that
 // interleave); the list's sequential narrowing is then six compare/selects over the same predicates as hit_rect
 // (a NaN t passes every comparison exactly as there).
-template <bool RECIP>
+template <int ARITH>
 __device__ __forceinline__ bool hit_box(f3 p0, f3 p1, const ray_t& r, const ray_recip& rr, float t_lo, float t_hi, float& t, int& face,
                                         bool* took_ieee = nullptr) {
     float tt[6];
     bool in[6];
     const float x[6] = {p1.z - r.o.z, p0.z - r.o.z, p1.y - r.o.y, p0.y - r.o.y, p1.x - r.o.x, p0.x - r.o.x};
     bool ieee = true;
-    if (RECIP) {
+    if (ARITH == ARITH_APPROX) {
+        tt[0] = x[0] * rr.inv.z; tt[1] = x[1] * rr.inv.z; tt[2] = x[2] * rr.inv.y; tt[3] = x[3] * rr.inv.y; tt[4] = x[4] * rr.inv.x; tt[5] = x[5] * rr.inv.x;
+        ieee = false;
+    } else if (ARITH == ARITH_RECIP) {
         tt[0] = div_by_recip(x[0], r.d.z, rr.inv.z); tt[1] = div_by_recip(x[1], r.d.z, rr.inv.z);
         tt[2] = div_by_recip(x[2], r.d.y, rr.inv.y); tt[3] = div_by_recip(x[3], r.d.y, rr.inv.y);
         tt[4] = div_by_recip(x[4], r.d.x, rr.inv.x); tt[5] = div_by_recip(x[5], r.d.x, rr.inv.x);
@@ -316,7 +342,7 @@ struct surf_hit_t { float t; int face; };  // face < 0: miss
 #ifndef RTNW_SURFACE_INLINE
 #define RTNW_SURFACE_INLINE __forceinline__
 #endif
-template <bool RECIP>
+template <int ARITH>
 __device__ RTNW_SURFACE_INLINE surf_hit_t hit_surface_rec(const rec* __restrict__ recs, const rtnw_xform_op* __restrict__ xforms, int i, float4 A,
                                                           float4 B, ray_t r, float a, ray_recip rr, float t_lo, float t_hi) {
     const uint32_t tag = __float_as_uint(B.z);
@@ -325,7 +351,7 @@ __device__ RTNW_SURFACE_INLINE surf_hit_t hit_surface_rec(const rec* __restrict_
     if (chain) {
         xform_ray(xforms, chain, r);
         a = dot(r.d, r.d);
-        if (RECIP) { rr.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z); rr.inv_a = 1.0f / a; }
+        if (ARITH != ARITH_IEEE) { rr.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z); rr.inv_a = 1.0f / a; }
     }
     surf_hit_t out;
     out.face = 0;
@@ -333,28 +359,31 @@ __device__ RTNW_SURFACE_INLINE surf_hit_t hit_surface_rec(const rec* __restrict_
     bool hit;
     switch (kind) {
         case K_SPHERE:
-            hit = RECIP ? hit_sphere_recip(mk3(A.x, A.y, A.z), A.w, r, a, rr.inv_a, t_lo, t_hi, out.t)
-                        : hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_lo, t_hi, out.t);
+            hit = ARITH == ARITH_APPROX  ? hit_sphere_approx(mk3(A.x, A.y, A.z), A.w, r, a, rr.inv_a, t_lo, t_hi, out.t)
+                  : ARITH == ARITH_RECIP ? hit_sphere_recip(mk3(A.x, A.y, A.z), A.w, r, a, rr.inv_a, t_lo, t_hi, out.t)
+                                         : hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_lo, t_hi, out.t);
             break;
         case K_MSPHERE: {
             const float4 A2 = __ldg(&recs[i + 1].a);
             const f3 c = moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
-            hit = RECIP ? hit_sphere_recip(c, A.w, r, a, rr.inv_a, t_lo, t_hi, out.t) : hit_sphere(c, A.w, r, a, t_lo, t_hi, out.t);
+            hit = ARITH == ARITH_APPROX  ? hit_sphere_approx(c, A.w, r, a, rr.inv_a, t_lo, t_hi, out.t)
+                  : ARITH == ARITH_RECIP ? hit_sphere_recip(c, A.w, r, a, rr.inv_a, t_lo, t_hi, out.t)
+                                         : hit_sphere(c, A.w, r, a, t_lo, t_hi, out.t);
             break;
         }
         case K_RECT_XY: hit = hit_rect<2, 0, 1>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
         case K_RECT_XZ: hit = hit_rect<1, 0, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
         case K_RECT_YZ: hit = hit_rect<0, 1, 2>(A.x, A.y, A.z, A.w, B.x, r, t_lo, t_hi, out.t); break;
-        case K_BOX: hit = hit_box<RECIP>(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, rr, t_lo, t_hi, out.t, out.face); break;
+        case K_BOX: hit = hit_box<ARITH>(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, rr, t_lo, t_hi, out.t, out.face); break;
         default: hit = false; break;
     }
     if (!hit) out.face = -1;
     return out;
 }
-template <bool RECIP = false>
+template <int ARITH = ARITH_IEEE>
 __device__ __forceinline__ bool hit_surface(const scene_view& S, int i, float4 A, float4 B, uint32_t tag, const ray_t& r_frame,
                                             float a_frame, float t_lo, float t_hi, float& t, int& face, const ray_recip& rr = ray_recip()) {
-    const surf_hit_t h = hit_surface_rec<RECIP>(S.recs, S.xforms, i, A, B, r_frame, a_frame, rr, t_lo, t_hi);
+    const surf_hit_t h = hit_surface_rec<ARITH>(S.recs, S.xforms, i, A, B, r_frame, a_frame, rr, t_lo, t_hi);
     t = h.t;
     face = h.face < 0 ? 0 : h.face;
     return h.face >= 0;
@@ -471,7 +500,7 @@ __device__ __forceinline__ bool hit_aabb6(float mnx, float mny, float mnz, float
 }
 
 // One primitive record (surface or medium) of a scope whose narrowing limit is `lim`; returns records consumed.
-template <bool COUNT, bool RECIP = false>
+template <bool COUNT, int ARITH = ARITH_IEEE>
 __device__ __forceinline__ int test_record(const scene_view& S, int i, float4 A, float4 B, const ray_t& r, float a, float t_min,
                                            float lim, const medium_key& mk, bool& hit, float& t, int& face, trav_counters& cnt,
                                            const ray_recip& rr = ray_recip()) {
@@ -483,13 +512,13 @@ __device__ __forceinline__ int test_record(const scene_view& S, int i, float4 A,
         hit = hit_medium(S, i, A, tag, r, a, t_min, lim, mk, t);
         return 1 + __float_as_int(A.z);
     }
-    hit = hit_surface<RECIP>(S, i, A, B, tag, r, a, t_min, lim, t, face, rr);
+    hit = hit_surface<ARITH>(S, i, A, B, tag, r, a, t_min, lim, t, face, rr);
     return kind == K_MSPHERE ? 2 : 1;
 }
 
 // A leaf of a bvh_node (one hitable, possibly a list of several primitives): tested with the UN-narrowed range the
 // node received, narrowing only inside the leaf (PSC/bvh.h:34-35, PSC/hitable_list.h:23-29).  Returns its candidate key.
-template <bool COUNT>
+template <bool COUNT, int ARITH>
 __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, float4 A, float4 B, const ray_t& r, float a, const ray_recip& rr,
                                             float t_min, float tmax0, const medium_key& mk, trav_counters& cnt) {
     hkey_t best = RTNW_KEY_NONE;
@@ -497,7 +526,7 @@ __device__ __forceinline__ hkey_t test_leaf(const scene_view& S, int first, floa
     int i = first;  // A, B: record `first`, loaded by the caller (both leaves of a gate are fetched before either is tested)
     for (;;) {
         bool hit; float t; int face;
-        const int step = test_record<COUNT, RTNW_RECIP != 0>(S, i, A, B, r, a, t_min, lim, mk, hit, t, face, cnt, rr);
+        const int step = test_record<COUNT, ARITH>(S, i, A, B, r, a, t_min, lim, mk, hit, t, face, cnt, rr);
         if (hit) { lim = t; best = make_key(t, i, face); }  // inside a list the later accepted hit always replaces
         if (__float_as_uint(B.z) & RTNW_TAG_LAST) break;
         i += step;
@@ -602,7 +631,7 @@ __device__ __forceinline__ void scan_run(const scene_view& S, int first, int nre
         for (int j = first; j < end; ++j) {
             const float4 A = __ldg(&S.recs[j].a), B = __ldg(&S.recs[j].b);
             float t; int face = 0;
-            if (hit_box<false>(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, ray_recip(), t_min, lim, t, face)) { lim = t; key = make_key(t, j, face); }
+            if (hit_box<ARITH_IEEE>(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), r, ray_recip(), t_min, lim, t, face)) { lim = t; key = make_key(t, j, face); }
         }
         if (COUNT) cnt.prim_tests += nrec;
     }
@@ -773,7 +802,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
     const int tid = threadIdx.x % GROUP;  // index within the cooperating group
     const unsigned lane = tid & 31u, lt_mask = (1u << lane) - 1u;
 #ifdef RTNW_ROUND_STATS
-    int stat_busy = 0; long long stat_c = 0; const long long stat_c0 = clock64();
+    int stat_busy = 0, stat_small = 0; long long stat_c = 0; const long long stat_c0 = clock64();
 #endif
     // The rounds of ALL items of a kernel form one sequence r = 0, 1, 2, ... (r3 = r % 3 lives in a register of every
     // thread).  Round r reads n[r3] / lh[r3], writes the popped state to buffer r3 + 1 and clears n[r3 + 2] — the buffer
@@ -844,7 +873,7 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
             if (take == 0) RTNW_STAT(3, 1);
             const int busy = node_threads + LPG * drain;
             RTNW_STAT(busy <= 64 ? 4 : busy <= 128 ? 5 : busy <= 192 ? 6 : 7, 1);
-            stat_busy = busy; stat_c = clock64();
+            stat_busy = busy; stat_c = clock64(); stat_small = n + LPG * queued <= 32 ? 1 : (n + LPG * queued <= 64 ? 2 : 0);
         }
 #endif
 #if !RTNW_PLAN1
@@ -961,14 +990,14 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
                 ray_recip rr; rr.inv = mk3(ri.x, ri.y, ri.z); rr.inv_a = ri.w;
                 medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
                 const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[own], ro.w)) : ro.w;
-                k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, rr, t_min, t_hi, mk, cnt);
+                k = test_leaf<COUNT, (FAST && RTNW_FAST_APPROX) ? ARITH_APPROX : (RTNW_RECIP ? ARITH_RECIP : ARITH_IEEE)>(S, leaf, A0, B0, r, rd.w, rr, t_min, t_hi, mk, cnt);
             }
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[own], k);
         }
         group_sync<GROUP>();
         r3 = nxt;
 #ifdef RTNW_ROUND_STATS
-        if (tid == 0) { const long long d = clock64() - stat_c; RTNW_STAT(stat_busy <= 64 ? 15 : stat_busy <= 128 ? 16 : stat_busy <= 192 ? 17 : 18, d); }
+        if (tid == 0) { const long long d = clock64() - stat_c; RTNW_STAT(stat_busy <= 64 ? 15 : stat_busy <= 128 ? 16 : stat_busy <= 192 ? 17 : 18, d); if (stat_small == 1) { RTNW_STAT(19, 1); RTNW_STAT(20, d); } else if (stat_small == 2) { RTNW_STAT(21, 1); RTNW_STAT(22, d); } }
 #endif
     }
 #ifdef RTNW_ROUND_STATS
@@ -1159,7 +1188,7 @@ __device__ __forceinline__ void async_bvh_item(const scene_view& S, SM& sm, int 
                     ray_t r; r.o = mk3(ro.x, ro.y, ro.z); r.d = mk3(rd.x, rd.y, rd.z); r.time = __uint_as_float(mq.w);
                     ray_recip rr; rr.inv = mk3(ri.x, ri.y, ri.z); rr.inv_a = ri.w;
                     medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
-                    const hkey_t k = test_leaf<COUNT>(S, leaf, A0, B0, r, rd.w, rr, t_min, ro.w, mk, cnt);
+                    const hkey_t k = test_leaf<COUNT, RTNW_RECIP ? ARITH_RECIP : ARITH_IEEE>(S, leaf, A0, B0, r, rd.w, rr, t_min, ro.w, mk, cnt);
                     if (k != RTNW_KEY_NONE) atomicMin(&sm.key[slot], k);
                 }
             }
@@ -1312,13 +1341,35 @@ struct surf_t { f3 p, n; float u, v; int mat; };
 // traversal only tracks (t, record) and the record is evaluated once here.
 // want_uv: the spherical (u,v) of PSC/hitable.h:14-19 costs an atan2f, an asinf and two double divisions, and only
 // image_texture::value reads u,v; the renderer asks for it only when the hit material's texture is an image.
-__device__ __forceinline__ void finish_hit(const scene_view& S, const ray_t& wr, const hit_t& h, surf_t& s, bool want_uv = true) {
+// REFINE (the fast mode, whose BVH leaves were tested with ARITH_APPROX): h.t of a sphere or box is replaced by the IEEE value
+// of the same root / face — what the reference computes for this primitive; a t that was exact already is reproduced.
+template <bool REFINE = false>
+__device__ __forceinline__ void finish_hit(const scene_view& S, const ray_t& wr, hit_t& h, surf_t& s, bool want_uv = true) {
     const float4 A = __ldg(&S.recs[h.rec].a), B = __ldg(&S.recs[h.rec].b);
     const uint32_t tag = __float_as_uint(B.z);
     const uint32_t kind = tag & 15u, chain = tag >> 8;
     ray_t r = wr;
     xform_ray(S.xforms, h.xf, r);
     xform_ray(S.xforms, chain, r);
+    if (REFINE) {
+        if (kind == K_SPHERE || kind == K_MSPHERE) {
+            f3 c = mk3(A.x, A.y, A.z);
+            if (kind == K_MSPHERE) {
+                const float4 A2 = __ldg(&S.recs[h.rec + 1].a);
+                c = moving_center(c, mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time);
+            }
+            const f3 oc = r.o - c;
+            const float a = dot(r.d, r.d), b = dot(oc, r.d), cc = dot(oc, oc) - A.w * A.w;
+            const float sq = sqrtf(b * b - a * cc);
+            const float q0 = (-b - sq) / a, q1 = (-b + sq) / a;
+            h.t = fabsf(q0 - h.t) <= fabsf(q1 - h.t) ? q0 : q1;
+        } else if (kind == K_BOX) {
+            const int axis = h.face >> 1;  // faces: +z -z +y -y +x -x (PSC/box.h:25-35)
+            const float k = (h.face & 1) ? (axis == 0 ? A.z : axis == 1 ? A.y : A.x) : (axis == 0 ? B.y : axis == 1 ? B.x : A.w);
+            const float o = axis == 0 ? r.o.z : axis == 1 ? r.o.y : r.o.x, d = axis == 0 ? r.d.z : axis == 1 ? r.d.y : r.d.x;
+            h.t = (k - o) / d;
+        }
+    }
     const float t = h.t;
     s.p = r.o + t * r.d;  // ray::point_at_parameter, PSC/ray.h:18
     s.u = 0.f; s.v = 0.f;  // the reference leaves u,v unwritten for moving spheres and media
