@@ -197,7 +197,13 @@ RENDER_CASES = [("ch01_random", 64, 32, 6), ("two_perlin", 64, 32, 6), ("cornell
                 ("earth", 40, 40, 4), ("random_scene", 64, 32, 6), ("test", 48, 24, 6)]
 
 
-@pytest.mark.parametrize("name,nx,ny,ns", RENDER_CASES)
+# every BASELINE.json config at its STATED image size (spp reduced to what the single-threaded reference renders in seconds):
+# the same per-path streams on both sides, so each of the 10^5..10^6 pixels is compared with the reference's own pixel
+FULL_SIZE_CASES = [("ch01_random", 200, 100, 2), ("two_perlin", 400, 200, 2), ("cornell_box", 500, 500, 1),
+                   ("cornell_smoke", 500, 500, 1), ("final+bvh", 1000, 1000, 1), ("final_northstar", 1000, 1000, 1)]
+
+
+@pytest.mark.parametrize("name,nx,ny,ns", RENDER_CASES + FULL_SIZE_CASES)
 def test_render_matches_reference_sample_for_sample(rtnw, ctx, name, nx, ny, ns):
     """Same Philox stream on both sides => the per-pixel SUMS agree except where a libm ulp flips a branch.
     Tolerance: >= 99% of pixels within 2e-5 relative (+1e-6 absolute) and total radiance within 0.2%.
