@@ -203,6 +203,9 @@ __device__ __forceinline__ void xform_hit_back(const rtnw_xform_op* __restrict__
 #ifndef RTNW_FAST_APPROX
 #define RTNW_FAST_APPROX 0
 #endif
+#ifndef RTNW_LEAF_DIRECT
+#define RTNW_LEAF_DIRECT 1
+#endif
 enum { ARITH_IEEE = 0, ARITH_RECIP = 1, ARITH_APPROX = 2 };
 struct ray_recip { f3 inv; float inv_a; };
 __device__ __forceinline__ float div_by_recip(float x, float d, float y) {
@@ -990,7 +993,25 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
                 ray_recip rr; rr.inv = mk3(ri.x, ri.y, ri.z); rr.inv_a = ri.w;
                 medium_key mk; mk.k0 = k0; mk.k1 = k1; mk.pixel = mq.x; mk.sample = mq.y; mk.depth = mq.z;
                 const float t_hi = FAST ? fminf(ro.w, key_t_or(sm.key[own], ro.w)) : ro.w;
-                k = test_leaf<COUNT, (FAST && RTNW_FAST_APPROX) ? ARITH_APPROX : (RTNW_RECIP ? ARITH_RECIP : ARITH_IEEE)>(S, leaf, A0, B0, r, rd.w, rr, t_min, t_hi, mk, cnt);
+                constexpr int ARITH = (FAST && RTNW_FAST_APPROX) ? ARITH_APPROX : (RTNW_RECIP ? ARITH_RECIP : ARITH_IEEE);
+#if RTNW_LEAF_DIRECT
+                // nearly every leaf is ONE plain box or sphere record (no transform chain, not a list, not a medium): those skip
+                // the record loop and the kind switch of the general leaf test — the same hit function, the same key
+                const uint32_t plain = __float_as_uint(B0.z) & ~(uint32_t)RTNW_TAG_FLIP;
+                if (plain == (K_BOX | RTNW_TAG_LAST)) {
+                    float t; int face = 0;
+                    if (COUNT) cnt.prim_tests++;
+                    if (hit_box<ARITH>(mk3(A0.x, A0.y, A0.z), mk3(A0.w, B0.x, B0.y), r, rr, t_min, t_hi, t, face)) k = make_key(t, leaf, face);
+                } else if (plain == (K_SPHERE | RTNW_TAG_LAST)) {
+                    float t;
+                    if (COUNT) cnt.prim_tests++;
+                    const bool hit = ARITH == ARITH_APPROX  ? hit_sphere_approx(mk3(A0.x, A0.y, A0.z), A0.w, r, rd.w, rr.inv_a, t_min, t_hi, t)
+                                     : ARITH == ARITH_RECIP ? hit_sphere_recip(mk3(A0.x, A0.y, A0.z), A0.w, r, rd.w, rr.inv_a, t_min, t_hi, t)
+                                                            : hit_sphere(mk3(A0.x, A0.y, A0.z), A0.w, r, rd.w, t_min, t_hi, t);
+                    if (hit) k = make_key(t, leaf, 0);
+                } else
+#endif
+                k = test_leaf<COUNT, ARITH>(S, leaf, A0, B0, r, rd.w, rr, t_min, t_hi, mk, cnt);
             }
             if (k != RTNW_KEY_NONE) atomicMin(&sm.key[own], k);
         }
