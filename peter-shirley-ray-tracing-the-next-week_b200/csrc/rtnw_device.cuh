@@ -206,6 +206,9 @@ __device__ __forceinline__ void xform_hit_back(const rtnw_xform_op* __restrict__
 #ifndef RTNW_LEAF_DIRECT
 #define RTNW_LEAF_DIRECT 1
 #endif
+#ifndef RTNW_LIST_DIRECT
+#define RTNW_LIST_DIRECT 1
+#endif
 enum { ARITH_IEEE = 0, ARITH_RECIP = 1, ARITH_APPROX = 2 };
 struct ray_recip { f3 inv; float inv_a; };
 __device__ __forceinline__ float div_by_recip(float x, float d, float y) {
@@ -1248,6 +1251,15 @@ __device__ __forceinline__ void scan_list_item(const scene_view& S, int i, int n
             j += 1 + nrec;
             continue;
         }
+#if RTNW_LIST_DIRECT
+        if ((__float_as_uint(B.z) & ~(uint32_t)(RTNW_TAG_FLIP | RTNW_TAG_CONT | RTNW_TAG_LAST)) == K_SPHERE) {  // a plain sphere: no chain, no switch
+            float t;
+            if (COUNT) cnt.prim_tests++;
+            if (hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
+            ++j;
+            continue;
+        }
+#endif
         bool hit; float t; int face;
         const int step = test_record<COUNT>(S, j, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
         if (hit) { lim = t; key = make_key(t, j, face); }  // list narrowing: an accepted hit is the new closest
