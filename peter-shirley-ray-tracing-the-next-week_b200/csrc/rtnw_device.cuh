@@ -209,6 +209,9 @@ __device__ __forceinline__ void xform_hit_back(const rtnw_xform_op* __restrict__
 #ifndef RTNW_LIST_DIRECT
 #define RTNW_LIST_DIRECT 1
 #endif
+#ifndef RTNW_MEDIUM_DIRECT
+#define RTNW_MEDIUM_DIRECT 1
+#endif
 enum { ARITH_IEEE = 0, ARITH_RECIP = 1, ARITH_APPROX = 2 };
 struct ray_recip { f3 inv; float inv_a; };
 __device__ __forceinline__ float div_by_recip(float x, float d, float y) {
@@ -422,11 +425,22 @@ __device__ __forceinline__ bool hit_medium(const scene_view& S, int i, float4 A,
     if (chain) { xform_ray(S.xforms, chain, r); a = dot(r.d, r.d); }
     const int nb = __float_as_int(A.z);
     float t1 = 0.f, t2 = 0.f;
+#if RTNW_MEDIUM_DIRECT
+    const float4 SA = __ldg(&S.recs[i + 1].a);
+    if (nb == 1 && (__float_as_uint(__ldg(&S.recs[i + 1].b).z) & ~(uint32_t)(RTNW_TAG_FLIP | RTNW_TAG_CONT | RTNW_TAG_LAST)) == K_SPHERE) {
+        // the boundary is one plain sphere (the media of final(), PSC/main.cpp:209-212): the two boundary->hit calls without
+        // the boundary loop and the kind switch
+        if (!hit_sphere(mk3(SA.x, SA.y, SA.z), SA.w, r, a, -FLT_MAX, FLT_MAX, t1)) return false;
+        if (!hit_sphere(mk3(SA.x, SA.y, SA.z), SA.w, r, a, (float)((double)t1 + 0.0001), FLT_MAX, t2)) return false;
+    } else
+#endif
+    {
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {  // rec1 over (-FLT_MAX, FLT_MAX), then rec2 over (rec1.t + 0.0001, FLT_MAX)
-        float tt;
-        if (!hit_boundary(S, i + 1, nb, r, a, pass ? (float)((double)t1 + 0.0001) : -FLT_MAX, FLT_MAX, tt)) return false;
-        if (pass) t2 = tt; else t1 = tt;
+        for (int pass = 0; pass < 2; ++pass) {  // rec1 over (-FLT_MAX, FLT_MAX), then rec2 over (rec1.t + 0.0001, FLT_MAX)
+            float tt;
+            if (!hit_boundary(S, i + 1, nb, r, a, pass ? (float)((double)t1 + 0.0001) : -FLT_MAX, FLT_MAX, tt)) return false;
+            if (pass) t2 = tt; else t1 = tt;
+        }
     }
     if (t1 < t_lo) t1 = t_lo;
     if (t2 > t_hi) t2 = t_hi;
