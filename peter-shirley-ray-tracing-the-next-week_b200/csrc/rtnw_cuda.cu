@@ -773,7 +773,7 @@ struct stream_builder {
                     if (boundary) return bad("constant_medium as the boundary of a constant_medium");
                     const int32_t bfirst = as_int(p.f[1]), bcount = as_int(p.f[2]);
                     const size_t at = recs.size();
-                    push(make_float4(p.f[0], p.f[3] /* leaf id bits */, 0, 0), 0, 0, RTNW_TAG(K_MEDIUM, flip, cont, chain), p.mat, id);
+                    push(make_float4(p.f[0], p.f[3] /* leaf id bits */, 0, -(1.0f / p.f[0])), 0, 0, RTNW_TAG(K_MEDIUM, flip, cont, chain), p.mat, id);
                     if (!emit_prims(bfirst, bcount, true, true)) return false;
                     recs[at].a.z = bits((int32_t)(recs.size() - at - 1));
                     for (size_t q = at + 1; q < recs.size(); ++q) leaf[q] = id;

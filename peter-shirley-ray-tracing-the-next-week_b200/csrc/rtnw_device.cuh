@@ -203,11 +203,14 @@ __device__ __forceinline__ void xform_hit_back(const rtnw_xform_op* __restrict__
 #ifndef RTNW_FAST_APPROX
 #define RTNW_FAST_APPROX 0
 #endif
+#ifndef RTNW_POP_FENCE
+#define RTNW_POP_FENCE 1
+#endif
 #ifndef RTNW_LEAF_DIRECT
 #define RTNW_LEAF_DIRECT 1
 #endif
 #ifndef RTNW_LIST_DIRECT
-#define RTNW_LIST_DIRECT 1
+#define RTNW_LIST_DIRECT 2
 #endif
 #ifndef RTNW_MEDIUM_DIRECT
 #define RTNW_MEDIUM_DIRECT 1
@@ -449,7 +452,7 @@ __device__ __forceinline__ bool hit_medium(const scene_view& S, int i, float4 A,
     const float len = sqrtf(a);  // r.direction().length(), same expression as dot(d,d)
     const float inside = (t2 - t1) * len;
     const float u = keyed_draw(mk.k0, mk.k1, mk.pixel, mk.sample, mk.depth, (uint32_t)__float_as_int(A.y));
-    const float hit_distance = (float)((double)(-(1.0f / A.x)) * log((double)u));
+    const float hit_distance = (float)((double)A.w * log((double)u));  // A.w = -(1 / density), rounded once on the host as PSC/constant_medium.h:42 does
     if (hit_distance < inside) {
         t = t1 + hit_distance / len;
         return true;
@@ -906,6 +909,14 @@ __device__ __forceinline__ void coop_bvh_item(const scene_view& S, SM& sm, int n
             // (no short-circuit): the four slab tests are independent and interleave; a lane of the last node warp
             // without a task reads node 0 / slot 0 and masks its results.
             const bool live = tid < take;
+#if RTNW_POP_FENCE
+            // The children this round pushes go to the stack slots this round pops ([base, base + take), stack discipline): every
+            // node warp must have READ its task before any of them pushes.  They all read right after the plan barrier and push
+            // hundreds of cycles later, so the order held by itself except about once in 10^8 warp-rounds, when a starved warp's
+            // read came after another warp's push (found as 1 differing path in ~5 % of 1000x1000 frames).  A barrier among
+            // the node warps alone, where they are still in step, makes it a guarantee.
+            if (GROUP > 32 && node_threads > 32) asm volatile("bar.sync 1, %0;" ::"r"(node_threads) : "memory");
+#endif
 #if RTNW_SMEM_NODES
             const uint32_t nbase = FAST ? (uint32_t)S.fast_node_base : 0u;
             const uint32_t nidx = live ? RTNW_TASK_IDX(task) : nbase;
@@ -1266,13 +1277,35 @@ __device__ __forceinline__ void scan_list_item(const scene_view& S, int i, int n
             continue;
         }
 #if RTNW_LIST_DIRECT
-        if ((__float_as_uint(B.z) & ~(uint32_t)(RTNW_TAG_FLIP | RTNW_TAG_CONT | RTNW_TAG_LAST)) == K_SPHERE) {  // a plain sphere: no chain, no switch
+        // plain records (no transform chain) skip the record dispatch: same test, same narrowing, same key
+        const uint32_t plain = __float_as_uint(B.z) & ~(uint32_t)(RTNW_TAG_FLIP | RTNW_TAG_CONT | RTNW_TAG_LAST);
+        if (plain == K_SPHERE) {
             float t;
             if (COUNT) cnt.prim_tests++;
             if (hit_sphere(mk3(A.x, A.y, A.z), A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
             ++j;
             continue;
         }
+#if RTNW_LIST_DIRECT >= 2
+        if (plain >= K_RECT_XY && plain <= K_RECT_YZ) {
+            float t;
+            if (COUNT) cnt.prim_tests++;
+            const bool hit = plain == K_RECT_XY   ? hit_rect<2, 0, 1>(A.x, A.y, A.z, A.w, B.x, r, t_min, lim, t)
+                             : plain == K_RECT_XZ ? hit_rect<1, 0, 2>(A.x, A.y, A.z, A.w, B.x, r, t_min, lim, t)
+                                                  : hit_rect<0, 1, 2>(A.x, A.y, A.z, A.w, B.x, r, t_min, lim, t);
+            if (hit) { lim = t; key = make_key(t, j, 0); }
+            ++j;
+            continue;
+        }
+        if (plain == K_MSPHERE) {
+            float t;
+            if (COUNT) cnt.prim_tests++;
+            const float4 A2 = __ldg(&S.recs[j + 1].a);
+            if (hit_sphere(moving_center(mk3(A.x, A.y, A.z), mk3(A2.x, A2.y, A2.z), B.x, B.y, r.time), A.w, r, a, t_min, lim, t)) { lim = t; key = make_key(t, j, 0); }
+            j += 2;
+            continue;
+        }
+#endif
 #endif
         bool hit; float t; int face;
         const int step = test_record<COUNT>(S, j, A, B, r, a, t_min, lim, mk, hit, t, face, cnt);
