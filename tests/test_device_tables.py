@@ -228,3 +228,15 @@ def test_inspect_rejects_bad_input():
     assert rtnw.device_lib().rtnw_scene_inspect(None, 0, None, 0) < 0
     t = rtnw.device_tables(hs.desc_ptr)  # a scene without a BVH: placeholder gate / node, records only
     assert len(t["recs"]) > 8 and (t["tag"] if "tag" in t else t["recs"][:, 6].view(np.uint32))[-1] & 15 == K_END
+
+
+@pytest.mark.parametrize("name", ["final_northstar", "cornell_smoke", "final"])
+def test_medium_records_carry_the_negated_reciprocal_density(name):
+    """PSC/constant_medium.h:42 computes -(1/density) in float for every sample; the upload rounds it once on the host
+    (IEEE float division, the same bits) and the kernels multiply by it: A.w of a medium record == -(1.0f / A.x)."""
+    _, t = _tables(name)
+    med = np.flatnonzero((t["tag"] & 15) == K_MEDIUM)
+    assert len(med) >= 2
+    rho = t["recs"][med, 0].astype(np.float32)
+    want = -(np.float32(1.0) / rho)
+    assert np.array_equal(t["recs"][med, 3].view(np.uint32), want.view(np.uint32)), (rho, t["recs"][med, 3])
